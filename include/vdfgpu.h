@@ -1,0 +1,153 @@
+/* vdfgpu.h -- C ABI of libvdfgpu.so: the B200 (sm_100a) data-parallel hot path of protocol/vdf's Nova
+ * prover for the MinRoot VDF.  Plain pointers and sizes only; every entry point names the reference
+ * interface it replaces.  The reference is pure Rust (src/minroot.rs, src/nova/proof.rs) and reaches the
+ * arithmetic below through nova-snark 0.8 / pasta-msm 0.1 / pasta_curves 0.4 (Cargo.toml:15,17,18); the
+ * Rust-side bindings a maintainer would add are shown in INTEGRATION.md.
+ *
+ * Data layouts (pasta_curves with feature "repr-c", Cargo.toml:17):
+ *   field element  32 B   four little-endian u64 limbs, Montgomery form (value * 2^256 mod m)
+ *   affine point   72 B   { x: 32 B, y: 32 B, infinity: u8, 7 B padding }
+ *   point          96 B   Jacobian { X, Y, Z }, identity <=> Z == 0.  Results are written normalised:
+ *                         (x, y, 1) or (0, 0, 0), so equal group elements have equal bytes.
+ *   State<F>       96 B   { x, y, i } (src/minroot.rs:267-272)
+ *
+ * Curves: VDFGPU_PALLAS (coordinates in Fp, scalars in Fq), VDFGPU_VESTA (coordinates in Fq, scalars in
+ * Fp).  Fields: VDFGPU_FP (Pallas base), VDFGPU_FQ (Pallas scalar; the field of PallasVDF,
+ * src/minroot.rs:38).
+ *
+ * Errors: every int-returning function returns 0 on success and a negative code on failure;
+ * vdfgpu_last_error() returns a thread-local message.  There is NO CPU fallback: without a usable CUDA
+ * device every compute call fails with VDFGPU_ERR_CUDA.
+ *
+ * Memory: "host" pointers are ordinary host memory owned by the caller for the duration of the call
+ * (pinned memory makes the copies faster); "_dev" entry points take device pointers and enqueue on the
+ * library stream (vdfgpu_set_stream) without synchronising.  Handles are owned by the library and freed
+ * by the matching *_destroy.  Calls on one thread are ordered; the library keeps no pointer after return.
+ */
+#ifndef VDFGPU_H
+#define VDFGPU_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VDFGPU_PALLAS 0
+#define VDFGPU_VESTA 1
+#define VDFGPU_FP 0
+#define VDFGPU_FQ 1
+
+#define VDFGPU_OK 0
+#define VDFGPU_ERR_ARG (-1)
+#define VDFGPU_ERR_CUDA (-2)
+#define VDFGPU_ERR_STATE (-3)
+
+/* generator-set flags */
+#define VDFGPU_GENS_TABLE 1u /* precompute 2^(c*w) * P_i levels (W x memory, one shared bucket set) */
+
+typedef struct vdfgpu_gens vdfgpu_gens;   /* device-resident commitment generators (nova CommitGens) */
+typedef struct vdfgpu_r1cs vdfgpu_r1cs;   /* device-resident R1CS shape in CSR (nova R1CSShape) */
+typedef struct vdfgpu_running vdfgpu_running;   /* device-resident running witness (nova RelaxedR1CSWitness) */
+
+/* ---- context -------------------------------------------------------------------------------------- */
+int vdfgpu_init(int device);              /* bind this process to one GPU (one process per GPU) */
+int vdfgpu_shutdown(void);
+int vdfgpu_device_count(void);
+const char* vdfgpu_last_error(void);
+const char* vdfgpu_version(void);
+int vdfgpu_set_stream(void* cuda_stream); /* cudaStream_t for all subsequent work; NULL = library stream */
+int vdfgpu_synchronize(void);
+uint64_t vdfgpu_launch_count(void);       /* kernels launched by this library so far */
+
+/* ---- a4: MSM.  Replaces pasta-msm's extern "C" mult_pippenger_{pallas,vesta}, the backend of nova's
+ * Group::vartime_multiscalar_mul used by commit(W) / commit(T) (reached from src/nova/proof.rs:342-349).
+ * Same symbol names and signature as pasta-msm 0.1.1 so its Rust wrapper links against this object. ---- */
+void mult_pippenger_pallas(void* out_point96, const void* points_affine72, size_t npoints,
+                           const void* scalars32, bool is_mont);
+void mult_pippenger_vesta(void* out_point96, const void* points_affine72, size_t npoints,
+                          const void* scalars32, bool is_mont);
+
+/* Generators are fixed for the life of PublicParams (src/nova/proof.rs:232-237): upload/repack once. */
+int vdfgpu_gens_create(int curve, const void* points_affine72_host, size_t n, uint32_t flags,
+                       uint32_t window_bits /* 0 = auto */, vdfgpu_gens** out);
+/* synthetic set P_i = (k0 + i*d) * G, G = (-1, 2), generated on the device (bench/tests);
+ * k0 and d are 32-byte little-endian canonical (non-Montgomery) integers */
+int vdfgpu_gens_progression(int curve, const void* k0_le32, const void* d_le32, size_t n, uint32_t flags,
+                            uint32_t window_bits, vdfgpu_gens** out);
+int vdfgpu_gens_export(const vdfgpu_gens* g, size_t first, size_t count, void* points_affine72_host);
+size_t vdfgpu_gens_len(const vdfgpu_gens* g);
+uint32_t vdfgpu_gens_window_bits(const vdfgpu_gens* g, size_t n);
+int vdfgpu_gens_destroy(vdfgpu_gens* g);
+
+/* commit(v) = sum_i v_i * gens[i] over the first n generators; scalars in Montgomery form */
+int vdfgpu_msm(vdfgpu_gens* g, const void* scalars32_host, size_t n, void* out_point96_host);
+int vdfgpu_msm_dev(vdfgpu_gens* g, const void* scalars32_dev, size_t n, void* out_point96_dev);
+/* point range [first, first+n) of the set: the shard a rank owns in the multi-GPU MSM */
+int vdfgpu_msm_range_dev(vdfgpu_gens* g, size_t first, const void* scalars32_dev, size_t n,
+                         void* out_point96_dev);
+/* out = sum of k points (combining per-GPU partial results; also instance-side additions) */
+int vdfgpu_point_sum(int curve, const void* points96_host, size_t k, void* out_point96_host);
+
+/* ---- a5-a7: R1CS.  Replaces nova-snark R1CSShape::{multiply_vec, commit_T} and
+ * RelaxedR1CSWitness::fold (reached from src/nova/proof.rs:342-349).  COO triples as nova stores them
+ * (row: usize, col: usize, val: Scalar); column j < vars is W[j], j == vars is u, j > vars is X. ---- */
+int vdfgpu_r1cs_create(int field, size_t num_cons, size_t num_vars, size_t num_io,
+                       const uint64_t* a_rows, const uint64_t* a_cols, const void* a_vals32, size_t a_nnz,
+                       const uint64_t* b_rows, const uint64_t* b_cols, const void* b_vals32, size_t b_nnz,
+                       const uint64_t* c_rows, const uint64_t* c_cols, const void* c_vals32, size_t c_nnz,
+                       vdfgpu_r1cs** out);
+int vdfgpu_r1cs_destroy(vdfgpu_r1cs* s);
+/* (Az, Bz, Cz) for z = [W | u | X] given as one host vector of vars+1+io elements */
+int vdfgpu_multiply_vec(const vdfgpu_r1cs* s, const void* z_host, void* Az_host, void* Bz_host,
+                        void* Cz_host);
+/* T = Az1.Bz2 + Az2.Bz1 - u1.Cz2 - u2.Cz1 (u2 = 1) and comm_T = MSM(T, gens); gens may be NULL to skip
+ * the commitment.  T_host may be NULL. */
+int vdfgpu_commit_T(const vdfgpu_r1cs* s, vdfgpu_gens* gens, const void* W1_host, const void* u1_host,
+                    const void* X1_host, const void* W2_host, const void* X2_host, void* T_host,
+                    void* comm_T_point96_host);
+/* W1 <- W1 + r*W2 (nW elements), E1 <- E1 + r*T (nE elements), in place on host buffers */
+int vdfgpu_fold(int field, void* W1_host, const void* W2_host, size_t nW, void* E1_host,
+                const void* T_host, size_t nE, const void* r32_host);
+
+/* Device-resident running instance for a chain of fold steps: W and E never leave HBM between steps.
+ * One step = what NIFS::prove does with the witness: commit_T against a fresh (W2, X2), then fold with
+ * the verifier challenge r (computed by the host random oracle from comm_T, so it arrives later). */
+int vdfgpu_running_create(const vdfgpu_r1cs* s, vdfgpu_gens* gens, vdfgpu_running** out);
+int vdfgpu_running_destroy(vdfgpu_running* f);
+int vdfgpu_running_set(vdfgpu_running* f, const void* W_host, const void* E_host, const void* u_host,
+                            const void* X_host);
+int vdfgpu_running_get(const vdfgpu_running* f, void* W_host, void* E_host, void* u_host, void* X_host);
+/* upload fresh witness, commit to it, compute T and comm_T; W2/T stay on the device for running_finish */
+int vdfgpu_running_commit(vdfgpu_running* f, const void* W2_host, const void* X2_host,
+                       void* comm_W2_point96_host, void* comm_T_point96_host);
+/* W <- W + r*W2, E <- E + r*T, u <- u + r, X <- X + r*X2 */
+int vdfgpu_running_finish(vdfgpu_running* f, const void* r32_host);
+
+/* ---- a8: batched MinRoot verification.  Replaces a loop of MinRootVDF::check (src/minroot.rs:369-371)
+ * / Evaluation::verify (:424-426) over independent chains.  ok_out[k] = 1 iff
+ * originals[k] == inverse_eval(results[k], t_k).  t_each may be NULL (then every chain uses t_uniform). */
+int vdfgpu_minroot_check_batch(int field, const void* results_state96_host,
+                               const void* originals_state96_host, const uint64_t* t_each,
+                               uint64_t t_uniform, size_t n, uint8_t* ok_out_host);
+int vdfgpu_minroot_check_batch_dev(int field, const void* results_dev, const void* originals_dev,
+                                   const uint64_t* t_each_dev, uint64_t t_uniform, size_t n,
+                                   uint8_t* ok_out_dev);
+/* out[k] = inverse_eval(results[k], t): the fast direction, also the step-circuit witness generator */
+int vdfgpu_minroot_inverse_eval_batch(int field, const void* results_state96_host, uint64_t t, size_t n,
+                                      void* out_state96_host);
+
+/* ---- measurement helpers (bench.py) ------------------------------------------------------------------ */
+/* elementwise field multiply out[i] = a[i]*b[i] iterated `iters` times (out <- out*b): field-layer parity
+ * tests and the integer-multiply roofline probe */
+int vdfgpu_field_mul_batch(int field, const void* a_host, const void* b_host, size_t n, uint32_t iters,
+                           void* out_host);
+/* register-only integer-multiply peak probe: returns 32x32->64 products per second in *out */
+int vdfgpu_imad_peak(double* mul32_per_s_wide, double* imad_per_s_lo, double* iadd3_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VDFGPU_H */

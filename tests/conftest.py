@@ -1,0 +1,49 @@
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with `pytest -m gpu` under gpurun)")
+
+
+def _has_gpu() -> bool:
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    # `-m gpu` on a box without a GPU must fail loudly, not skip: the product has no CPU fallback.
+    pass
+
+
+@pytest.fixture(scope="session")
+def emul():
+    """tests/emul/libvdf_emul.so: the kernel functors run by a CPU loop (test tool, see emul.cpp)."""
+    import ctypes
+    src = ROOT / "tests" / "emul" / "emul.cpp"
+    lib = ROOT / "tests" / "emul" / "libvdf_emul.so"
+    deps = [src] + list((ROOT / "vdf_b200" / "csrc").glob("*.cuh")) + list((ROOT / "vdf_b200" / "csrc").glob("*.hpp"))
+    if not lib.exists() or any(d.stat().st_mtime > lib.stat().st_mtime for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                        "-o", str(lib), str(src)], check=True)
+    return ctypes.CDLL(str(lib))
+
+
+@pytest.fixture(scope="session")
+def gpu_lib():
+    """libvdfgpu.so bound to cuda:0; fails (not skips) when the extension or the GPU is missing."""
+    from vdf_b200 import _lib
+    lib = _lib.load()
+    _lib.check(lib.vdfgpu_init(0))
+    return lib

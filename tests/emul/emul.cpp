@@ -1,0 +1,178 @@
+// tests/emul: CPU execution of the library's kernel functors through vdf::HostLaunch.
+//
+// TEST TOOL ONLY.  libvdfgpu.so never contains or calls this code; the product has no CPU path.  The
+// point is to let `pytest -m "not gpu"` check the pipeline *logic* that surrounds the PTX field
+// arithmetic -- signed-digit recoding, the counting sort, range-based bucket accumulation with its record
+// fix-up levels, the bucket-reduction tree, COO->CSR, the cross-term and fold formulas -- against the
+// Python oracle in a container that has no GPU.  Field multiplication here is the portable 64-bit C path of
+// field.cuh; the PTX path is checked on the GPU (tests/test_gpu_field.py).
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../vdf_b200/csrc/minroot.cuh"
+#include "../../vdf_b200/csrc/msm.cuh"
+#include "../../vdf_b200/csrc/r1cs.cuh"
+#include "../../vdf_b200/csrc/r1cs_host.hpp"
+
+using namespace vdf;
+
+namespace {
+
+template <class F>
+void field_op(int op, const fe* a, const fe* b, fe* out, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    switch (op) {
+      case 0: out[i] = F::mul(a[i], b[i]); break;
+      case 1: out[i] = F::add(a[i], b[i]); break;
+      case 2: out[i] = F::sub(a[i], b[i]); break;
+      case 3: out[i] = F::sqr(a[i]); break;
+      case 4: out[i] = F::inv(a[i]); break;
+      case 5: out[i] = F::from_mont(a[i]); break;
+      case 6: out[i] = F::neg(a[i]); break;
+      case 7: out[i] = F::one(); break;
+    }
+  }
+}
+
+MsmPlan plan_for(size_t n, size_t stride, int table, uint32_t c, uint32_t S, uint32_t G, uint32_t logm, int is_mont) {
+  MsmPlan p;
+  p.n = (uint32_t)n;
+  p.table = table ? 1u : 0u;
+  p.c = c;
+  p.W = msm_windows(c);
+  p.B = 1u << (c - 1);
+  p.NB = table ? 1u : p.W;
+  p.level_stride = stride;
+  p.S = S;
+  p.G = G;
+  p.logm = logm;
+  p.is_mont = is_mont ? 1u : 0u;
+  return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+int emul_field_op(int field, int op, const void* a, const void* b, void* out, size_t n) {
+  if (field == 0) field_op<Fp>(op, (const fe*)a, (const fe*)b, (fe*)out, n);
+  else field_op<Fq>(op, (const fe*)a, (const fe*)b, (fe*)out, n);
+  return 0;
+}
+
+// full MSM pipeline; points in pasta_curves 72-byte layout; table != 0 builds the 2^(c w) levels first
+int emul_msm(int curve, int table, uint32_t c, uint32_t S, uint32_t G, uint32_t logm, const void* affine72, size_t n,
+             const void* scalars, int is_mont, void* out96) {
+  HostLaunch L;
+  uint32_t W = table ? msm_windows(c) : 1;
+  std::vector<affine_t> pts((size_t)W * (n ? n : 1));
+  L.run(n, RepackFn{(const uint8_t*)affine72, pts.data()});
+  if (table)
+    for (uint32_t l = 1; l < W; l++) {
+      size_t threads = (n + 7) / 8;
+      if (curve == 0) L.run(threads, TableLevelFn<Pallas, Fp>{pts.data() + (size_t)(l - 1) * n, pts.data() + (size_t)l * n, n, c});
+      else L.run(threads, TableLevelFn<Vesta, Fq>{pts.data() + (size_t)(l - 1) * n, pts.data() + (size_t)l * n, n, c});
+    }
+  MsmPlan p = plan_for(n, n, table, c, S, G, logm, is_mont);
+  std::vector<fe> sc(n ? n : 1);
+  std::memcpy(sc.data(), scalars, n * 32);
+  jac_t out;
+  if (curve == 0) msm_run<HostLaunch, Pallas, Fq>(L, p, pts.data(), sc.data(), &out);
+  else msm_run<HostLaunch, Vesta, Fp>(L, p, pts.data(), sc.data(), &out);
+  std::memcpy(out96, &out, 96);
+  return 0;
+}
+
+int emul_progression(int curve, const void* k0, const void* d, size_t n, void* out72) {
+  HostLaunch L;
+  fe fk0, fd;
+  std::memcpy(fk0.v, k0, 32);
+  std::memcpy(fd.v, d, 32);
+  ProgSetup setup;
+  std::vector<affine_t> pts(n ? n : 1);
+  size_t threads = (n + PROG_CH - 1) / PROG_CH;
+  if (curve == 0) {
+    L.run(1, ProgressionSetupFn<Pallas, Fp>{fk0, fd, &setup});
+    L.run(threads, ProgressionFn<Pallas, Fp>{&setup, pts.data(), n});
+  } else {
+    L.run(1, ProgressionSetupFn<Vesta, Fq>{fk0, fd, &setup});
+    L.run(threads, ProgressionFn<Vesta, Fq>{&setup, pts.data(), n});
+  }
+  L.run(n, UnpackFn{pts.data(), (uint8_t*)out72});
+  return 0;
+}
+
+int emul_point_sum(int curve, const void* pts96, size_t k, void* out96) {
+  HostLaunch L;
+  jac_t out;
+  if (curve == 0) L.run(1, JacSumFn<Pallas>{(const jac_t*)pts96, (uint32_t)k, &out});
+  else L.run(1, JacSumFn<Vesta>{(const jac_t*)pts96, (uint32_t)k, &out});
+  std::memcpy(out96, &out, 96);
+  return 0;
+}
+
+int emul_minroot_check(int field, const void* results, const void* originals, const uint64_t* t_each,
+                       uint64_t t_uniform, size_t n, uint8_t* ok) {
+  HostLaunch L;
+  if (field == 0) L.run(n, MinRootCheckFn<Fp>{(const state_t*)results, (const state_t*)originals, t_each, t_uniform, ok});
+  else L.run(n, MinRootCheckFn<Fq>{(const state_t*)results, (const state_t*)originals, t_each, t_uniform, ok});
+  return 0;
+}
+
+int emul_minroot_inverse_eval(int field, const void* results, uint64_t t, size_t n, void* out) {
+  HostLaunch L;
+  if (field == 0) L.run(n, MinRootInverseEvalFn<Fp>{(const state_t*)results, t, (state_t*)out});
+  else L.run(n, MinRootInverseEvalFn<Fq>{(const state_t*)results, t, (state_t*)out});
+  return 0;
+}
+
+// R1CS: mode 0 = multiply_vec (out = Az|Bz|Cz, 3*cons elements, z1 only), mode 1 = cross-term T (cons elements)
+int emul_r1cs(int field, int mode, size_t num_cons, size_t num_vars, size_t num_io, const uint64_t* a_rows,
+              const uint64_t* a_cols, const void* a_vals, size_t a_nnz, const uint64_t* b_rows, const uint64_t* b_cols,
+              const void* b_vals, size_t b_nnz, const uint64_t* c_rows, const uint64_t* c_cols, const void* c_vals,
+              size_t c_nnz, const void* W1, const void* u1, const void* X1, const void* W2, const void* X2, void* out) {
+  const uint64_t* rows[3] = {a_rows, b_rows, c_rows};
+  const uint64_t* cols[3] = {a_cols, b_cols, c_cols};
+  const uint8_t* vals[3] = {(const uint8_t*)a_vals, (const uint8_t*)b_vals, (const uint8_t*)c_vals};
+  size_t nnzs[3] = {a_nnz, b_nnz, c_nnz};
+  HostCsr csr;
+  try {
+    csr = coo_to_csr(num_cons, num_vars + 1 + num_io, rows, cols, vals, nnzs);
+  } catch (const std::exception&) {
+    return -1;
+  }
+  std::vector<fe> val(csr.val.size() / 32 + 1);
+  std::memcpy(val.data(), csr.val.data(), csr.val.size());
+  CsrView m{csr.row_ptr.data(), csr.col.data(), val.data(), (uint32_t)num_cons, (uint32_t)num_vars, (uint32_t)num_io};
+  HostLaunch L;
+  std::vector<fe> w1(num_vars + 1), w2(num_vars + 1), ux1(1 + num_io), ux2(1 + num_io);
+  std::memcpy(w1.data(), W1, num_vars * 32);
+  std::memcpy(ux1.data(), u1, 32);
+  std::memcpy(ux1.data() + 1, X1, num_io * 32);
+  ZView z1{w1.data(), ux1.data(), ux1.data() + 1};
+  fe* o = (fe*)out;
+  if (mode == 0) {
+    if (field == 0) L.run(3 * num_cons, MultiplyVecFn<Fp>{m, z1, o, o + num_cons, o + 2 * num_cons});
+    else L.run(3 * num_cons, MultiplyVecFn<Fq>{m, z1, o, o + num_cons, o + 2 * num_cons});
+    return 0;
+  }
+  std::memcpy(w2.data(), W2, num_vars * 32);
+  ux2[0] = field == 0 ? Fp::one() : Fq::one();
+  std::memcpy(ux2.data() + 1, X2, num_io * 32);
+  ZView z2{w2.data(), ux2.data(), ux2.data() + 1};
+  if (field == 0) L.run(num_cons, CrossTermFn<Fp>{m, z1, z2, o});
+  else L.run(num_cons, CrossTermFn<Fq>{m, z1, z2, o});
+  return 0;
+}
+
+int emul_fold(int field, void* W1, const void* W2, size_t nW, void* E1, const void* T, size_t nE, const void* r) {
+  HostLaunch L;
+  fe rr;
+  std::memcpy(&rr, r, 32);
+  if (field == 0) L.run(nW + nE, FoldFn<Fp>{(fe*)W1, (const fe*)W2, nW, (fe*)E1, (const fe*)T, nE, &rr});
+  else L.run(nW + nE, FoldFn<Fq>{(fe*)W1, (const fe*)W2, nW, (fe*)E1, (const fe*)T, nE, &rr});
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+"""GPU parity for the Pippenger MSM through the C ABI: bit-exact canonical points
+against the Python oracle at small sizes, the known-discrete-log identity at BASELINE sizes, linearity,
+edge cases (empty, zeros, identity points, duplicates, P and -P, non-Montgomery scalars)."""
+import random
+
+import pytest
+
+from oracle import pasta as O
+from vdf_b200 import msm as G
+from vdf_b200.encoding import CURVE_BASE
+from tests.util import nova_like_scalars, rand_scalars
+
+pytestmark = pytest.mark.gpu
+
+CURVES = [O.CURVE_PALLAS, O.CURVE_VESTA]
+
+
+@pytest.mark.parametrize("cid", CURVES)
+def test_progression_matches_oracle(gpu_lib, cid):
+    cv = O.CURVES[cid]
+    g = G.Generators.progression(cid, 7, 3, 100)
+    assert g.export() == cv.progression(7, 3, 100)
+    assert all(cv.on_curve(p) for p in g.export())
+    g2 = G.Generators.progression(cid, 0, 5, 40)  # starts at the identity
+    assert g2.export() == cv.progression(0, 5, 40)
+
+
+@pytest.mark.parametrize("cid", CURVES)
+@pytest.mark.parametrize("table", [False, True])
+def test_msm_small_vs_oracle(gpu_lib, cid, table):
+    cv = O.CURVES[cid]
+    rng = O.XorShiftRng()
+    n = 700
+    pts = cv.progression(5, 11, n)
+    sc = rand_scalars(rng, cv.order, n)
+    sc[0], sc[1], sc[2], sc[3] = 0, 1, cv.order - 1, 1 << 128
+    pts[7] = None                       # identity generator
+    pts[9], sc[9] = pts[8], sc[8]       # duplicate point, same scalar (doubling inside a bucket)
+    pts[11], sc[11] = cv.neg(pts[10]), sc[10]  # P and -P cancel
+    want = O.jac_to_bytes(cv, cv.msm(sc, pts))
+    for wb in (0, 5, 9, 13):
+        g = G.Generators.from_points(cid, pts, table=table, window_bits=wb)
+        assert g.commit_bytes(O.fes_to_bytes(sc, cv.order)) == want, (cid, table, wb)
+        # prefix commits (nova commits to vectors shorter than the generator set)
+        for k in (0, 1, 2, 33, 699):
+            assert g.commit_bytes(O.fes_to_bytes(sc[:k], cv.order)) == O.jac_to_bytes(cv, cv.msm(sc[:k], pts[:k]))
+        g.close()
+
+
+@pytest.mark.parametrize("cid", CURVES)
+def test_mult_pippenger_abi(gpu_lib, cid):
+    """pasta-msm's symbol: points travel with the call; is_mont both ways."""
+    cv = O.CURVES[cid]
+    rng = O.XorShiftRng()
+    n = 300
+    pts = cv.progression(3, 7, n)
+    sc = rand_scalars(rng, cv.order, n)
+    want = O.jac_to_bytes(cv, cv.msm(sc, pts))
+    pb = O.affines_to_bytes(cv, pts)
+    assert G.mult_pippenger(cid, pb, O.fes_to_bytes(sc, cv.order), True) == want
+    assert G.mult_pippenger(cid, pb, b"".join(s.to_bytes(32, "little") for s in sc), False) == want
+    assert G.mult_pippenger(cid, b"", b"", True) == bytes(96)
+
+
+@pytest.mark.parametrize("table", [False, True])
+def test_msm_nova_like_scalars(gpu_lib, table):
+    """Witness-like digits (many 0/1/small): one bucket gets ~n/4 entries -> exercises the record levels."""
+    cv = O.PALLAS
+    rng, py = O.XorShiftRng(), random.Random(5)
+    n = 1 << 14
+    k0, d = 12345, 678
+    sc = nova_like_scalars(py, rng, cv.order, n)
+    g = G.Generators.progression(cv.cid, k0, d, n, table=table)
+    assert g.commit(sc) == cv.msm_known_dlog(sc, k0, d)
+
+
+@pytest.mark.parametrize("cid", CURVES)
+@pytest.mark.parametrize("table,log2n", [(False, 16), (True, 16), (False, 20), (True, 20)])
+def test_msm_known_dlog_large(gpu_lib, cid, table, log2n):
+    """BASELINE config 2 sizes: P_i = (k0 + i d) G  =>  MSM = (sum s_i (k0 + i d)) G, checked in O(n)."""
+    cv = O.CURVES[cid]
+    n = 1 << log2n
+    k0, d = 0x1234567, 0x89ABCDEF01
+    py = random.Random(log2n * 7 + cid)
+    sc = [py.randrange(cv.order) for _ in range(n)]
+    g = G.Generators.progression(cid, k0, d, n, table=table)
+    got = g.commit(sc)
+    assert got == cv.msm_known_dlog(sc, k0, d)
+    # linearity: MSM(s + s') = MSM(s) + MSM(s')
+    sc2 = [py.randrange(cv.order) for _ in range(n)]
+    got2 = g.commit(sc2)
+    got12 = g.commit([(a + b) % cv.order for a, b in zip(sc, sc2)])
+    assert got12 == cv.add(got, got2)
+    g.close()
+
+
+def test_point_sum_and_sharded_combine(gpu_lib):
+    """Multi-GPU path emulated as G point-range slices on one GPU: partials combined with
+    vdfgpu_point_sum equal the single-range result."""
+    cv = O.PALLAS
+    n, world = 1 << 12, 4
+    k0, d = 99, 5
+    py = random.Random(3)
+    sc = [py.randrange(cv.order) for _ in range(n)]
+    full = G.Generators.progression(cv.cid, k0, d, n)
+    want = full.commit_bytes(O.fes_to_bytes(sc, cv.order))
+    parts = []
+    per = n // world
+    for r in range(world):
+        shard = G.Generators.progression(cv.cid, k0 + r * per * d, d, per, table=True)
+        parts.append(shard.commit_bytes(O.fes_to_bytes(sc[r * per:(r + 1) * per], cv.order)))
+    assert G.point_sum(cv.cid, b"".join(parts)) == want
+    assert G.point_sum(cv.cid, b"") == bytes(96)
+    assert O.jac_from_bytes(cv, want) == cv.msm_known_dlog(sc, k0, d)
+
+
+def test_msm_argument_errors(gpu_lib):
+    from vdf_b200 import VdfGpuError
+    g = G.Generators.progression(0, 1, 1, 16)
+    with pytest.raises(VdfGpuError):
+        g.commit_bytes(bytes(32 * 17))  # more scalars than generators
+    with pytest.raises(VdfGpuError):
+        G.Generators.from_affine_bytes(0, b"", table=False)

@@ -1,0 +1,157 @@
+"""CPU: pins the oracle.  The reference holds no golden values for this path, so the pins
+are (1) the reference's own constants and addition chains, (2) its round-trip tests restated, (3) algebraic
+identities between independent oracle routines, (4) the frozen fixtures under tests/golden."""
+import json
+from pathlib import Path
+
+import pytest
+
+from oracle import pasta as O
+
+GOLDEN = Path(__file__).parent / "golden" / "vectors.json"
+
+
+def test_moduli_and_reference_constants():
+    # src/minroot.rs:273-285: 5 * INVALPHA == 1 mod (m - 1), and INVALPHA == (4(m-1)+1)/5
+    for limbs, m in ((O.FP_RESCUE_INVALPHA, O.P), (O.FQ_RESCUE_INVALPHA, O.Q)):
+        e = O.limbs_to_int(limbs)
+        assert 5 * e % (m - 1) == 1
+        assert e == (4 * (m - 1) + 1) // 5
+        assert m.bit_length() == 255 and (m - 1) % 5 == 1
+        assert (-pow(m, -1, 1 << 32)) % (1 << 32) == 0xFFFFFFFF
+    assert O.P % (1 << 128) != O.Q % (1 << 128) and O.P >> 128 == O.Q >> 128 == 1 << 126
+
+
+def test_exponents():  # src/minroot.rs:449-458
+    assert O.PallasVDF().inverse_exponent == 5 and O.VestaVDF().inverse_exponent == 5
+
+
+@pytest.mark.parametrize("mk", [O.PallasVDF, O.VestaVDF])
+def test_steps(mk):  # src/minroot.rs:460-477, plus the reference's addition chains (:88-127, :223-261)
+    rng = O.XorShiftRng()
+    vdf = mk()
+    for _ in range(100):
+        x = O.field_random(rng, vdf.m)
+        y = vdf.forward_step(x)
+        assert vdf.inverse_step(y) == x
+        assert vdf.forward_step_addition_chain(x) == y
+
+
+def test_eval():  # src/minroot.rs:479-510
+    rng = O.XorShiftRng()
+    vdf = O.PallasVDF()
+    for _ in range(10):
+        x = O.State(O.field_random(rng, vdf.m), O.field_random(rng, vdf.m), 0)
+        result = vdf.eval(x, 10)
+        assert vdf.inverse_eval(result, 10) == x
+        assert vdf.check(result, 10, x)
+
+
+@pytest.mark.parametrize("mk", [O.PallasVDF, O.VestaVDF])
+def test_vanilla_proof(mk):  # src/minroot.rs:512-542
+    rng = O.XorShiftRng()
+    vdf = mk()
+    x = O.State(O.field_random(rng, vdf.m), 0, 0)
+    t, n = 4, 3
+    _, final = O.Evaluation.eval(vdf, x, t)
+    for _ in range(1, n):
+        _, new = O.Evaluation.eval(vdf, final.result, t)
+        final = final.append(new)
+        assert final is not None
+    assert vdf.element(final.t) == final.result.i and final.t == n * t and final.verify(x)
+
+
+def test_xorshift_generator():
+    # rand_xorshift: state words are the seed's four LE u32s; first output from the documented recurrence
+    rng = O.XorShiftRng()
+    x = 0x2A2A2A2A
+    t = (x ^ (x << 11)) & 0xFFFFFFFF
+    assert rng.next_u32() == (x ^ (x >> 19) ^ (t ^ (t >> 8))) & 0xFFFFFFFF
+
+
+@pytest.mark.parametrize("cv", [O.PALLAS, O.VESTA])
+def test_curve_group_law(cv):
+    g = cv.gen
+    assert cv.on_curve(g)
+    assert cv.mul(cv.order, g) is None and cv.mul(cv.order - 1, g) == cv.neg(g)
+    a, b = cv.mul(12345, g), cv.mul(67890, g)
+    assert cv.add(a, b) == cv.mul(12345 + 67890, g) and cv.add(a, cv.neg(a)) is None
+    assert cv.add(a, a) == cv.mul(2 * 12345, g)
+    # byte layouts round-trip
+    assert O.affine_from_bytes(cv, O.affine_to_bytes(cv, a)) == a
+    assert O.affine_from_bytes(cv, O.affine_to_bytes(cv, None)) is None
+    assert O.jac_from_bytes(cv, O.jac_to_bytes(cv, a)) == a and O.jac_from_bytes(cv, bytes(96)) is None
+
+
+@pytest.mark.parametrize("cv", [O.PALLAS, O.VESTA])
+def test_msm_three_ways(cv):
+    rng = O.XorShiftRng()
+    n = 48
+    pts = cv.progression(9, 4, n)
+    sc = [O.field_random(rng, cv.order) for _ in range(n)]
+    a = cv.msm_naive(sc, pts)
+    assert a == cv.msm(sc, pts) == cv.msm(sc, pts, c=5) == cv.msm_known_dlog(sc, 9, 4)
+
+
+@pytest.mark.parametrize("t", [5, 10, 100])
+def test_step_circuit_shape(t):  # src/nova/proof.rs:87-230; dimensions of SURVEY.md section 8
+    vdf = O.PallasVDF()
+    rng = O.XorShiftRng()
+    s0 = O.State(O.field_random(rng, vdf.m), 0, 1)
+    res = vdf.eval(s0, t)
+    shape, W, X, outs = O.make_step_instance(O.FIELD_FQ, t, res)
+    assert shape.num_cons == 3 * t + 1
+    assert shape.num_vars == 4 * t + 1 + 3            # + the three z_in variables
+    assert (len(shape.A), len(shape.B), len(shape.C)) == (3 * t + 1, 3 * t + 1, 6 * t + 2)
+    assert outs == s0                                  # circuit output == inverse_eval(result, t)
+    assert shape.is_sat_relaxed(W, [0] * shape.num_cons, 1, X)
+    Wbad = list(W)
+    Wbad[5] = (Wbad[5] + 1) % vdf.m
+    assert not shape.is_sat_relaxed(Wbad, [0] * shape.num_cons, 1, X)
+
+
+def test_fold_preserves_relaxed_satisfiability():
+    vdf = O.PallasVDF()
+    rng = O.XorShiftRng()
+    s = vdf.eval(O.State(O.field_random(rng, vdf.m), 0, 1), 10)
+    shape, W, X, _ = O.make_step_instance(O.FIELD_FQ, 10, s, aug_cons=40)
+    E, u = [0] * shape.num_cons, 1
+    for k in range(2):
+        s = vdf.eval(s, 10)
+        _, W2, X2, _ = O.make_step_instance(O.FIELD_FQ, 10, s, aug_cons=40)
+        T = shape.cross_term(W, u, X, W2, X2)
+        r = O.field_random(rng, vdf.m) >> 127
+        W, E = O.fold_vec(W, W2, r, vdf.m), O.fold_vec(E, T, r, vdf.m)
+        u, X = (u + r) % vdf.m, [(a + r * b) % vdf.m for a, b in zip(X, X2)]
+        assert shape.is_sat_relaxed(W, E, u, X)
+
+
+def test_golden_vectors():
+    """Frozen known-answer vectors (tests/golden/make_golden.py): any drift in the oracle shows here."""
+    g = json.loads(GOLDEN.read_text())
+    for fname, m in (("fp", O.P), ("fq", O.Q)):
+        for a, b, ab_mont in g["field_mul_mont"][fname]:
+            a, b = int(a, 16), int(b, 16)
+            assert O.fe_to_bytes(a * b % m, m).hex() == ab_mont
+    for name, mk in (("pallas", O.PallasVDF), ("vesta", O.VestaVDF)):
+        vdf = mk()
+        for rec in g["minroot"][name]:
+            s = O.State(*[int(v, 16) for v in rec["start"]])
+            r = vdf.eval(s, rec["t"])
+            assert [hex(r.x), hex(r.y), hex(r.i)] == rec["result"]
+            assert vdf.check(r, rec["t"], s)
+    for cname, cv in (("pallas", O.PALLAS), ("vesta", O.VESTA)):
+        rec = g["msm"][cname]
+        rng = O.XorShiftRng()
+        sc = [O.field_random(rng, cv.order) for _ in range(rec["n"])]
+        pts = cv.progression(rec["k0"], rec["d"], rec["n"])
+        assert O.jac_to_bytes(cv, cv.msm(sc, pts)).hex() == rec["result_point96"]
+    rec = g["cross_term"]
+    vdf = O.PallasVDF()
+    rng = O.XorShiftRng()
+    s = vdf.eval(O.State(O.field_random(rng, vdf.m), 0, 1), rec["t"])
+    shape, W1, X1, _ = O.make_step_instance(O.FIELD_FQ, rec["t"], s, aug_cons=rec["aug"])
+    _, W2, X2, _ = O.make_step_instance(O.FIELD_FQ, rec["t"], vdf.eval(s, rec["t"]), aug_cons=rec["aug"])
+    T = shape.cross_term(W1, int(rec["u1"], 16), X1, W2, X2)
+    import hashlib
+    assert hashlib.sha256(O.fes_to_bytes(T, vdf.m)).hexdigest() == rec["T_sha256"]

@@ -1,0 +1,546 @@
+// C ABI, part 1: context, generator sets, MSM, batched MinRoot verification, measurement probes.
+// See include/vdfgpu.h for the contract and the reference interfaces each entry point replaces.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "ctx.cuh"
+#include "minroot.cuh"
+
+namespace vdf {
+
+static thread_local std::string g_error;
+
+Context& ctx() {
+  static Context c;
+  return c;
+}
+
+void set_error(const std::string& msg) { g_error = msg; }
+
+static void init_locked(int device) {
+  Context& c = ctx();
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    throw std::runtime_error(std::string("no usable CUDA device (there is no CPU fallback): ") +
+                             cudaGetErrorString(e));
+  if (device < 0 || device >= count) throw ArgError("vdfgpu_init: device index out of range");
+  if (c.ready && c.device == device) return;
+  if (c.ready) throw StateError("vdfgpu_init: already bound to another device (one process per GPU)");
+  VDF_CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  VDF_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    throw std::runtime_error("vdfgpu: kernels are built for sm_100a only; found compute capability " +
+                             std::to_string(prop.major) + "." + std::to_string(prop.minor));
+  VDF_CUDA_CHECK(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+  // keep freed blocks in the stream-ordered pool: the MSM allocates its workspace per call
+  cudaMemPool_t pool;
+  VDF_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t threshold = UINT64_MAX;
+  VDF_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+  c.stream = c.own_stream;
+  c.device = device;
+  c.ready = true;
+}
+
+void require_ready() {
+  if (!ctx().ready) init_locked(0);
+  VDF_CUDA_CHECK(cudaSetDevice(ctx().device));
+}
+
+// ---- MSM dispatch -----------------------------------------------------------------------------------
+static MsmPlan make_plan(const vdfgpu_gens* g, size_t n, bool is_mont) {
+  MsmPlan p;
+  p.n = (uint32_t)n;
+  p.table = (g->flags & VDFGPU_GENS_TABLE) ? 1u : 0u;
+  p.c = p.table ? g->c : msm_pick_c(n, false);
+  p.W = msm_windows(p.c);
+  p.B = 1u << (p.c - 1);
+  p.NB = p.table ? 1u : p.W;
+  p.level_stride = g->n;
+  p.is_mont = is_mont ? 1u : 0u;
+  // entries per accumulate thread: enough threads to fill 148 SMs, ranges long enough to amortise
+  // the two boundary records each thread may emit
+  size_t E = n * p.W;
+  size_t S = E / (148 * 768);
+  if (S < 32) S = 32;
+  if (S > 128) S = 128;
+  p.S = (uint32_t)S;
+  if (const char* s = std::getenv("VDFGPU_MSM_S")) p.S = (uint32_t)std::atoi(s);
+  p.G = 16;
+  p.logm = 3;
+  return p;
+}
+
+void msm_on_device(vdfgpu_gens* g, size_t first, const fe* d_scalars, size_t n, jac_t* d_out, bool is_mont) {
+  if (first + n > g->n) throw ArgError("msm: more scalars than generators");
+  Context& c = ctx();
+  CudaLaunch L(c.stream);
+  MsmPlan p = make_plan(g, n, is_mont);
+  // point references are 31 bits (+ sign), sorted positions 32 bits
+  if ((uint64_t)p.W * (p.table ? g->n : n) >= (1ull << 31)) throw ArgError("msm: n too large for 31-bit point references");
+  const affine_t* pts = g->pts + first;
+  if (g->curve == VDFGPU_PALLAS) msm_run<CudaLaunch, Pallas, Fq>(L, p, pts, d_scalars, d_out);
+  else msm_run<CudaLaunch, Vesta, Fp>(L, p, pts, d_scalars, d_out);
+  c.launches += L.launches;
+}
+
+static void build_table(vdfgpu_gens* g, CudaLaunch& L) {
+  // levels 1..W-1: level[l] = 2^c * level[l-1]
+  for (uint32_t l = 1; l < g->W; l++) {
+    const affine_t* prev = g->pts + (size_t)(l - 1) * g->n;
+    affine_t* next = g->pts + (size_t)l * g->n;
+    size_t threads = (g->n + 7) / 8;
+    if (g->curve == VDFGPU_PALLAS) L.run<128>(threads, TableLevelFn<Pallas, Fp>{prev, next, g->n, g->c});
+    else L.run<128>(threads, TableLevelFn<Vesta, Fq>{prev, next, g->n, g->c});
+  }
+}
+
+static vdfgpu_gens* gens_alloc(int curve, size_t n, uint32_t flags, uint32_t window_bits) {
+  if (curve != VDFGPU_PALLAS && curve != VDFGPU_VESTA) throw ArgError("gens: unknown curve");
+  if (n == 0) throw ArgError("gens: empty generator set");
+  if (window_bits != 0 && (window_bits < 2 || window_bits > 24)) throw ArgError("gens: window_bits out of range");
+  vdfgpu_gens* g = new vdfgpu_gens();
+  g->curve = curve;
+  g->n = n;
+  g->flags = flags;
+  bool table = flags & VDFGPU_GENS_TABLE;
+  g->c = window_bits ? window_bits : msm_pick_c(n, table);
+  g->W = table ? msm_windows(g->c) : 1;
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, (size_t)g->W * n * sizeof(affine_t));
+  if (e != cudaSuccess) {
+    delete g;
+    throw std::runtime_error(std::string("gens: cudaMalloc failed: ") + cudaGetErrorString(e));
+  }
+  g->pts = reinterpret_cast<affine_t*>(p);
+  return g;
+}
+
+template <class F>
+static void minroot_check_dispatch(CudaLaunch& L, const void* res, const void* orig, const uint64_t* t_each,
+                                   uint64_t t_uniform, size_t n, uint8_t* ok) {
+  L.run<128>(n, MinRootCheckFn<F>{reinterpret_cast<const state_t*>(res), reinterpret_cast<const state_t*>(orig),
+                                  t_each, t_uniform, ok});
+}
+
+template <class F>
+struct FieldMulFn {
+  const fe* a; const fe* b; fe* out; uint32_t iters;
+  VDF_HD void operator()(size_t i) const {
+    fe x = fe_load(a + i), y = fe_load(b + i);
+#pragma unroll 1
+    for (uint32_t k = 0; k < iters; k++) x = F::mul(x, y);
+    fe_store(out + i, x);
+  }
+};
+
+// ---- integer pipe probes --------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) imad_probe_kernel(uint32_t* sink, uint32_t seed, int iters) {
+  uint32_t a = seed + threadIdx.x, b = seed * 3u + blockIdx.x;
+  if (MODE == 0) {  // IMAD.WIDE.U32: 32x32 + 64 -> 64, eight independent accumulators
+    uint64_t acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = k + a;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a), "r"(b));
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= acc[k];
+    if (s == 0x1234567ull) sink[0] = (uint32_t)s;
+  } else if (MODE == 1) {  // IMAD (low 32 bits)
+    uint32_t acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = k + a;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(a), "r"(b));
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= acc[k];
+    if (s == 0x1234567u) sink[0] = s;
+  } else {  // IADD3
+    uint32_t acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = k + a;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) asm volatile("add.u32 %0, %0, %1;" : "+r"(acc[k]) : "r"(b));
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= acc[k];
+    if (s == 0x1234567u) sink[0] = s;
+  }
+}
+
+template <int MODE>
+static double probe_rate(cudaStream_t st, uint32_t* sink) {
+  const int blocks = 148 * 8, iters = 4096;
+  cudaEvent_t e0, e1;
+  VDF_CUDA_CHECK(cudaEventCreate(&e0));
+  VDF_CUDA_CHECK(cudaEventCreate(&e1));
+  for (int w = 0; w < 2; w++) imad_probe_kernel<MODE><<<blocks, 256, 0, st>>>(sink, 12345u, iters);
+  VDF_CUDA_CHECK(cudaEventRecord(e0, st));
+  imad_probe_kernel<MODE><<<blocks, 256, 0, st>>>(sink, 12345u, iters);
+  VDF_CUDA_CHECK(cudaEventRecord(e1, st));
+  VDF_CUDA_CHECK(cudaEventSynchronize(e1));
+  float ms = 0;
+  VDF_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  double ops = (double)blocks * 256.0 * iters * 32.0;
+  return ops / (ms * 1e-3);
+}
+
+}  // namespace vdf
+
+using namespace vdf;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int vdfgpu_init(int device) {
+  return guarded([&] { init_locked(device); });
+}
+
+int vdfgpu_shutdown(void) {
+  return guarded([&] {
+    Context& c = ctx();
+    if (!c.ready) return;
+    cudaStreamSynchronize(c.stream);
+    if (c.own_stream) cudaStreamDestroy(c.own_stream);
+    c.own_stream = nullptr;
+    c.stream = nullptr;
+    c.ready = false;
+    c.device = -1;
+  });
+}
+
+int vdfgpu_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+  return count;
+}
+
+const char* vdfgpu_last_error(void) { return g_error.c_str(); }
+
+const char* vdfgpu_version(void) { return "vdfgpu 0.1 (sm_100a)"; }
+
+int vdfgpu_set_stream(void* cuda_stream) {
+  return guarded([&] {
+    require_ready();
+    Context& c = ctx();
+    c.stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c.own_stream;
+  });
+}
+
+int vdfgpu_synchronize(void) {
+  return guarded([&] {
+    require_ready();
+    VDF_CUDA_CHECK(cudaStreamSynchronize(ctx().stream));
+  });
+}
+
+uint64_t vdfgpu_launch_count(void) { return ctx().launches; }
+
+// ---- generator sets ------------------------------------------------------------------------------------
+int vdfgpu_gens_create(int curve, const void* points_affine72_host, size_t n, uint32_t flags,
+                       uint32_t window_bits, vdfgpu_gens** out) {
+  return guarded([&] {
+    if (!out || !points_affine72_host) throw ArgError("gens_create: null pointer");
+    require_ready();
+    Context& c = ctx();
+    vdfgpu_gens* g = gens_alloc(curve, n, flags, window_bits);
+    try {
+      CudaLaunch L(c.stream);
+      DevBuf<uint8_t> raw(n * 72, c.stream);
+      h2d(raw.p, points_affine72_host, n * 72, c.stream);
+      L.run<256>(n, RepackFn{raw.p, g->pts});
+      if (flags & VDFGPU_GENS_TABLE) build_table(g, L);
+      c.launches += L.launches;
+      VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    } catch (...) {
+      cudaFree(g->pts);
+      delete g;
+      throw;
+    }
+    *out = g;
+  });
+}
+
+int vdfgpu_gens_progression(int curve, const void* k0_le32, const void* d_le32, size_t n, uint32_t flags,
+                            uint32_t window_bits, vdfgpu_gens** out) {
+  return guarded([&] {
+    if (!out || !k0_le32 || !d_le32) throw ArgError("gens_progression: null pointer");
+    require_ready();
+    Context& c = ctx();
+    vdfgpu_gens* g = gens_alloc(curve, n, flags, window_bits);
+    try {
+      CudaLaunch L(c.stream);
+      fe k0, d;
+      std::memcpy(k0.v, k0_le32, 32);
+      std::memcpy(d.v, d_le32, 32);
+      DevBuf<ProgSetup> setup(1, c.stream);
+      size_t threads = (n + PROG_CH - 1) / PROG_CH;
+      if (threads >= (1ull << 32)) throw ArgError("gens_progression: n too large");
+      if (curve == VDFGPU_PALLAS) {
+        L.run<32>(1, ProgressionSetupFn<Pallas, Fp>{k0, d, setup.p});
+        L.run<128>(threads, ProgressionFn<Pallas, Fp>{setup.p, g->pts, n});
+      } else {
+        L.run<32>(1, ProgressionSetupFn<Vesta, Fq>{k0, d, setup.p});
+        L.run<128>(threads, ProgressionFn<Vesta, Fq>{setup.p, g->pts, n});
+      }
+      if (flags & VDFGPU_GENS_TABLE) build_table(g, L);
+      c.launches += L.launches;
+      VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    } catch (...) {
+      cudaFree(g->pts);
+      delete g;
+      throw;
+    }
+    *out = g;
+  });
+}
+
+int vdfgpu_gens_export(const vdfgpu_gens* g, size_t first, size_t count, void* points_affine72_host) {
+  return guarded([&] {
+    if (!g || !points_affine72_host) throw ArgError("gens_export: null pointer");
+    if (first + count > (size_t)g->W * g->n) throw ArgError("gens_export: range out of bounds");
+    require_ready();
+    Context& c = ctx();
+    CudaLaunch L(c.stream);
+    DevBuf<uint8_t> raw(count * 72, c.stream);
+    L.run<256>(count, UnpackFn{g->pts + first, raw.p});
+    d2h(points_affine72_host, raw.p, count * 72, c.stream);
+    c.launches += L.launches;
+    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  });
+}
+
+size_t vdfgpu_gens_len(const vdfgpu_gens* g) { return g ? g->n : 0; }
+
+uint32_t vdfgpu_gens_window_bits(const vdfgpu_gens* g, size_t n) {
+  if (!g) return 0;
+  return (g->flags & VDFGPU_GENS_TABLE) ? g->c : msm_pick_c(n, false);
+}
+
+int vdfgpu_gens_destroy(vdfgpu_gens* g) {
+  return guarded([&] {
+    if (!g) return;
+    if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+    cudaFree(g->pts);
+    delete g;
+  });
+}
+
+// ---- MSM -------------------------------------------------------------------------------------------------
+int vdfgpu_msm(vdfgpu_gens* g, const void* scalars32_host, size_t n, void* out_point96_host) {
+  return guarded([&] {
+    if (!g || !out_point96_host || (n && !scalars32_host)) throw ArgError("msm: null pointer");
+    require_ready();
+    Context& c = ctx();
+    DevBuf<fe> sc(n ? n : 1, c.stream);
+    DevBuf<jac_t> res(1, c.stream);
+    h2d(sc.p, scalars32_host, n * 32, c.stream);
+    msm_on_device(g, 0, sc.p, n, res.p, true);
+    d2h(out_point96_host, res.p, sizeof(jac_t), c.stream);
+    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  });
+}
+
+int vdfgpu_msm_dev(vdfgpu_gens* g, const void* scalars32_dev, size_t n, void* out_point96_dev) {
+  return guarded([&] {
+    if (!g || !out_point96_dev || (n && !scalars32_dev)) throw ArgError("msm_dev: null pointer");
+    require_ready();
+    msm_on_device(g, 0, reinterpret_cast<const fe*>(scalars32_dev), n, reinterpret_cast<jac_t*>(out_point96_dev),
+                  true);
+  });
+}
+
+int vdfgpu_msm_range_dev(vdfgpu_gens* g, size_t first, const void* scalars32_dev, size_t n,
+                         void* out_point96_dev) {
+  return guarded([&] {
+    if (!g || !out_point96_dev || (n && !scalars32_dev)) throw ArgError("msm_range_dev: null pointer");
+    if (g->flags & VDFGPU_GENS_TABLE && first != 0)
+      throw ArgError("msm_range_dev: table-mode sets are sharded by creating one set per rank");
+    require_ready();
+    msm_on_device(g, first, reinterpret_cast<const fe*>(scalars32_dev), n,
+                  reinterpret_cast<jac_t*>(out_point96_dev), true);
+  });
+}
+
+int vdfgpu_point_sum(int curve, const void* points96_host, size_t k, void* out_point96_host) {
+  return guarded([&] {
+    if (!out_point96_host || (k && !points96_host)) throw ArgError("point_sum: null pointer");
+    if (curve != VDFGPU_PALLAS && curve != VDFGPU_VESTA) throw ArgError("point_sum: unknown curve");
+    require_ready();
+    Context& c = ctx();
+    CudaLaunch L(c.stream);
+    DevBuf<jac_t> in(k ? k : 1, c.stream);
+    DevBuf<jac_t> res(1, c.stream);
+    h2d(in.p, points96_host, k * sizeof(jac_t), c.stream);
+    if (curve == VDFGPU_PALLAS) L.run<32>(1, JacSumFn<Pallas>{in.p, (uint32_t)k, res.p});
+    else L.run<32>(1, JacSumFn<Vesta>{in.p, (uint32_t)k, res.p});
+    d2h(out_point96_host, res.p, sizeof(jac_t), c.stream);
+    c.launches += L.launches;
+    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  });
+}
+
+static void mult_pippenger(int curve, void* out, const void* points, size_t npoints, const void* scalars,
+                           bool is_mont) {
+  int rc = guarded([&] {
+    if (!out || (npoints && (!points || !scalars))) throw ArgError("mult_pippenger: null pointer");
+    require_ready();
+    Context& c = ctx();
+    if (npoints == 0) {
+      std::memset(out, 0, 96);
+      return;
+    }
+    vdfgpu_gens g;
+    g.curve = curve;
+    g.n = npoints;
+    g.flags = 0;
+    g.W = 1;
+    CudaLaunch L(c.stream);
+    DevBuf<uint8_t> raw(npoints * 72, c.stream);
+    DevBuf<affine_t> pts(npoints, c.stream);
+    DevBuf<fe> sc(npoints, c.stream);
+    DevBuf<jac_t> res(1, c.stream);
+    h2d(raw.p, points, npoints * 72, c.stream);
+    h2d(sc.p, scalars, npoints * 32, c.stream);
+    L.run<256>(npoints, RepackFn{raw.p, pts.p});
+    c.launches += L.launches;
+    g.pts = pts.p;
+    msm_on_device(&g, 0, sc.p, npoints, res.p, is_mont);
+    d2h(out, res.p, sizeof(jac_t), c.stream);
+    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  });
+  if (rc != VDFGPU_OK) {
+    // pasta-msm's entry point is infallible (void); its Rust wrapper panics on misuse.  Mirror that.
+    std::fprintf(stderr, "mult_pippenger: %s\n", vdfgpu_last_error());
+    std::abort();
+  }
+}
+
+void mult_pippenger_pallas(void* out, const void* points, size_t npoints, const void* scalars, bool is_mont) {
+  mult_pippenger(VDFGPU_PALLAS, out, points, npoints, scalars, is_mont);
+}
+
+void mult_pippenger_vesta(void* out, const void* points, size_t npoints, const void* scalars, bool is_mont) {
+  mult_pippenger(VDFGPU_VESTA, out, points, npoints, scalars, is_mont);
+}
+
+// ---- batched MinRoot verification -----------------------------------------------------------------------
+int vdfgpu_minroot_check_batch_dev(int field, const void* results_dev, const void* originals_dev,
+                                   const uint64_t* t_each_dev, uint64_t t_uniform, size_t n,
+                                   uint8_t* ok_out_dev) {
+  return guarded([&] {
+    if (field != VDFGPU_FP && field != VDFGPU_FQ) throw ArgError("minroot_check: unknown field");
+    if (n && (!results_dev || !originals_dev || !ok_out_dev)) throw ArgError("minroot_check: null pointer");
+    require_ready();
+    Context& c = ctx();
+    CudaLaunch L(c.stream);
+    if (field == VDFGPU_FP) minroot_check_dispatch<Fp>(L, results_dev, originals_dev, t_each_dev, t_uniform, n, ok_out_dev);
+    else minroot_check_dispatch<Fq>(L, results_dev, originals_dev, t_each_dev, t_uniform, n, ok_out_dev);
+    c.launches += L.launches;
+  });
+}
+
+int vdfgpu_minroot_check_batch(int field, const void* results_host, const void* originals_host,
+                               const uint64_t* t_each, uint64_t t_uniform, size_t n, uint8_t* ok_out_host) {
+  return guarded([&] {
+    if (field != VDFGPU_FP && field != VDFGPU_FQ) throw ArgError("minroot_check: unknown field");
+    if (n && (!results_host || !originals_host || !ok_out_host)) throw ArgError("minroot_check: null pointer");
+    if (n == 0) return;
+    require_ready();
+    Context& c = ctx();
+    CudaLaunch L(c.stream);
+    DevBuf<state_t> res(n, c.stream), orig(n, c.stream);
+    DevBuf<uint64_t> tt(t_each ? n : 1, c.stream);
+    DevBuf<uint8_t> ok(n, c.stream);
+    h2d(res.p, results_host, n * sizeof(state_t), c.stream);
+    h2d(orig.p, originals_host, n * sizeof(state_t), c.stream);
+    if (t_each) h2d(tt.p, t_each, n * 8, c.stream);
+    const uint64_t* tp = t_each ? tt.p : nullptr;
+    if (field == VDFGPU_FP) minroot_check_dispatch<Fp>(L, res.p, orig.p, tp, t_uniform, n, ok.p);
+    else minroot_check_dispatch<Fq>(L, res.p, orig.p, tp, t_uniform, n, ok.p);
+    d2h(ok_out_host, ok.p, n, c.stream);
+    c.launches += L.launches;
+    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  });
+}
+
+int vdfgpu_minroot_inverse_eval_batch(int field, const void* results_host, uint64_t t, size_t n,
+                                      void* out_host) {
+  return guarded([&] {
+    if (field != VDFGPU_FP && field != VDFGPU_FQ) throw ArgError("minroot_inverse_eval: unknown field");
+    if (n && (!results_host || !out_host)) throw ArgError("minroot_inverse_eval: null pointer");
+    if (n == 0) return;
+    require_ready();
+    Context& c = ctx();
+    CudaLaunch L(c.stream);
+    DevBuf<state_t> res(n, c.stream), out(n, c.stream);
+    h2d(res.p, results_host, n * sizeof(state_t), c.stream);
+    if (field == VDFGPU_FP) L.run<128>(n, MinRootInverseEvalFn<Fp>{res.p, t, out.p});
+    else L.run<128>(n, MinRootInverseEvalFn<Fq>{res.p, t, out.p});
+    d2h(out_host, out.p, n * sizeof(state_t), c.stream);
+    c.launches += L.launches;
+    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  });
+}
+
+// ---- probes ---------------------------------------------------------------------------------------------
+int vdfgpu_field_mul_batch(int field, const void* a_host, const void* b_host, size_t n, uint32_t iters,
+                           void* out_host) {
+  return guarded([&] {
+    if (field != VDFGPU_FP && field != VDFGPU_FQ) throw ArgError("field_mul_batch: unknown field");
+    if (n && (!a_host || !b_host || !out_host)) throw ArgError("field_mul_batch: null pointer");
+    if (n == 0) return;
+    require_ready();
+    Context& c = ctx();
+    CudaLaunch L(c.stream);
+    DevBuf<fe> a(n, c.stream), b(n, c.stream), o(n, c.stream);
+    h2d(a.p, a_host, n * 32, c.stream);
+    h2d(b.p, b_host, n * 32, c.stream);
+    if (field == VDFGPU_FP) L.run<256>(n, FieldMulFn<Fp>{a.p, b.p, o.p, iters});
+    else L.run<256>(n, FieldMulFn<Fq>{a.p, b.p, o.p, iters});
+    d2h(out_host, o.p, n * 32, c.stream);
+    c.launches += L.launches;
+    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  });
+}
+
+int vdfgpu_imad_peak(double* mul32_per_s_wide, double* imad_per_s_lo, double* iadd3_per_s) {
+  return guarded([&] {
+    require_ready();
+    Context& c = ctx();
+    DevBuf<uint32_t> sink(4, c.stream);
+    double w = probe_rate<0>(c.stream, sink.p);
+    double l = probe_rate<1>(c.stream, sink.p);
+    double a = probe_rate<2>(c.stream, sink.p);
+    c.launches += 9;
+    if (mul32_per_s_wide) *mul32_per_s_wide = w;
+    if (imad_per_s_lo) *imad_per_s_lo = l;
+    if (iadd3_per_s) *iadd3_per_s = a;
+  });
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,329 @@
+// C ABI, part 2: R1CS shape upload (COO -> CSR), multiply_vec, commit_T, fold, and the device-resident
+// running instance used for a chain of fold steps.  Contract and reference pointers: include/vdfgpu.h.
+#include <cstring>
+#include <vector>
+
+#include "ctx.cuh"
+#include "r1cs.cuh"
+#include "r1cs_host.hpp"
+
+struct vdfgpu_r1cs {
+  int field = 0;
+  uint32_t cons = 0, vars = 0, io = 0;
+  size_t nnz = 0;
+  uint32_t* row_ptr = nullptr;  // [3*cons+1]
+  uint32_t* col = nullptr;
+  vdf::fe* val = nullptr;
+  vdf::CsrView view() const { return vdf::CsrView{row_ptr, col, val, cons, vars, io}; }
+};
+
+struct vdfgpu_running {
+  const vdfgpu_r1cs* shape = nullptr;
+  vdfgpu_gens* gens = nullptr;
+  vdf::fe* W = nullptr;   // running witness [vars]
+  vdf::fe* E = nullptr;   // running error   [cons]
+  vdf::fe* uX = nullptr;  // [1 + io]: u then X
+  vdf::fe* W2 = nullptr;  // fresh witness  [vars]
+  vdf::fe* uX2 = nullptr; // [1 + io]: 1 then X2
+  vdf::fe* T = nullptr;   // cross-term [cons]
+  vdf::fe* r = nullptr;   // challenge
+  vdf::jac_t* comm = nullptr;  // [2] comm_W2, comm_T
+  bool have_running = false, have_fresh = false;
+};
+
+namespace vdf {
+
+template <class Fn0, class Fn1>
+static void by_field(int field, Fn0 fp, Fn1 fq) {
+  if (field == VDFGPU_FP) fp();
+  else fq();
+}
+
+static void launch_multiply_vec(CudaLaunch& L, const vdfgpu_r1cs* s, ZView z, fe* Az, fe* Bz, fe* Cz) {
+  size_t rows = 3 * (size_t)s->cons;
+  if (s->field == VDFGPU_FP) L.run<128>(rows, MultiplyVecFn<Fp>{s->view(), z, Az, Bz, Cz});
+  else L.run<128>(rows, MultiplyVecFn<Fq>{s->view(), z, Az, Bz, Cz});
+}
+
+static void launch_cross_term(CudaLaunch& L, const vdfgpu_r1cs* s, ZView z1, ZView z2, fe* T) {
+  if (s->field == VDFGPU_FP) L.run<128>(s->cons, CrossTermFn<Fp>{s->view(), z1, z2, T});
+  else L.run<128>(s->cons, CrossTermFn<Fq>{s->view(), z1, z2, T});
+}
+
+static void launch_fold(CudaLaunch& L, int field, fe* W1, const fe* W2, size_t nW, fe* E1, const fe* T, size_t nE,
+                        const fe* r) {
+  if (field == VDFGPU_FP) L.run<256>(nW + nE, FoldFn<Fp>{W1, W2, nW, E1, T, nE, r});
+  else L.run<256>(nW + nE, FoldFn<Fq>{W1, W2, nW, E1, T, nE, r});
+}
+
+// the scalar field of the commitment curve must be the R1CS field
+static void check_gens_field(const vdfgpu_r1cs* s, const vdfgpu_gens* g) {
+  int scalar_field = g->curve == VDFGPU_PALLAS ? VDFGPU_FQ : VDFGPU_FP;
+  if (scalar_field != s->field) throw ArgError("generator curve's scalar field differs from the R1CS field");
+}
+
+static fe host_one(int field) { return field == VDFGPU_FP ? Fp::one() : Fq::one(); }
+
+}  // namespace vdf
+
+using namespace vdf;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int vdfgpu_r1cs_create(int field, size_t num_cons, size_t num_vars, size_t num_io,
+                       const uint64_t* a_rows, const uint64_t* a_cols, const void* a_vals32, size_t a_nnz,
+                       const uint64_t* b_rows, const uint64_t* b_cols, const void* b_vals32, size_t b_nnz,
+                       const uint64_t* c_rows, const uint64_t* c_cols, const void* c_vals32, size_t c_nnz,
+                       vdfgpu_r1cs** out) {
+  return guarded([&] {
+    if (!out) throw ArgError("r1cs_create: null out");
+    if (field != VDFGPU_FP && field != VDFGPU_FQ) throw ArgError("r1cs_create: unknown field");
+    if (num_cons == 0 || num_cons >= (1ull << 30) || num_vars >= (1ull << 31)) throw ArgError("r1cs_create: bad dimensions");
+    const uint64_t* rows[3] = {a_rows, b_rows, c_rows};
+    const uint64_t* cols[3] = {a_cols, b_cols, c_cols};
+    const uint8_t* vals[3] = {(const uint8_t*)a_vals32, (const uint8_t*)b_vals32, (const uint8_t*)c_vals32};
+    size_t nnzs[3] = {a_nnz, b_nnz, c_nnz};
+    size_t nnz = a_nnz + b_nnz + c_nnz;
+    if (nnz >= (1ull << 32)) throw ArgError("r1cs_create: too many non-zeros");
+    const size_t ncols = num_vars + 1 + num_io;
+    HostCsr csr;
+    try {
+      csr = coo_to_csr(num_cons, ncols, rows, cols, vals, nnzs);
+    } catch (const std::invalid_argument& e) {
+      throw ArgError(std::string("r1cs_create: ") + e.what());
+    }
+    require_ready();
+    const size_t R = 3 * num_cons;
+    std::vector<uint32_t>& row_ptr = csr.row_ptr;
+    std::vector<uint32_t>& col = csr.col;
+    std::vector<uint8_t>& val = csr.val;
+    vdfgpu_r1cs* s = new vdfgpu_r1cs();
+    s->field = field;
+    s->cons = (uint32_t)num_cons;
+    s->vars = (uint32_t)num_vars;
+    s->io = (uint32_t)num_io;
+    s->nnz = nnz;
+    Context& c = ctx();
+    try {
+      VDF_CUDA_CHECK(cudaMalloc((void**)&s->row_ptr, (R + 1) * 4));
+      VDF_CUDA_CHECK(cudaMalloc((void**)&s->col, (nnz ? nnz : 1) * 4));
+      VDF_CUDA_CHECK(cudaMalloc((void**)&s->val, (nnz ? nnz : 1) * 32));
+      h2d(s->row_ptr, row_ptr.data(), (R + 1) * 4, c.stream);
+      h2d(s->col, col.data(), nnz * 4, c.stream);
+      h2d(s->val, val.data(), nnz * 32, c.stream);
+      VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    } catch (...) {
+      cudaFree(s->row_ptr); cudaFree(s->col); cudaFree(s->val);
+      delete s;
+      throw;
+    }
+    *out = s;
+  });
+}
+
+int vdfgpu_r1cs_destroy(vdfgpu_r1cs* s) {
+  return guarded([&] {
+    if (!s) return;
+    if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+    cudaFree(s->row_ptr); cudaFree(s->col); cudaFree(s->val);
+    delete s;
+  });
+}
+
+int vdfgpu_multiply_vec(const vdfgpu_r1cs* s, const void* z_host, void* Az_host, void* Bz_host, void* Cz_host) {
+  return guarded([&] {
+    if (!s || !z_host || !Az_host || !Bz_host || !Cz_host) throw ArgError("multiply_vec: null pointer");
+    require_ready();
+    Context& c = ctx();
+    CudaLaunch L(c.stream);
+    size_t nz = (size_t)s->vars + 1 + s->io;
+    DevBuf<fe> z(nz, c.stream), out(3 * (size_t)s->cons, c.stream);
+    h2d(z.p, z_host, nz * 32, c.stream);
+    ZView zv{z.p, z.p + s->vars, z.p + s->vars + 1};
+    launch_multiply_vec(L, s, zv, out.p, out.p + s->cons, out.p + 2 * (size_t)s->cons);
+    d2h(Az_host, out.p, (size_t)s->cons * 32, c.stream);
+    d2h(Bz_host, out.p + s->cons, (size_t)s->cons * 32, c.stream);
+    d2h(Cz_host, out.p + 2 * (size_t)s->cons, (size_t)s->cons * 32, c.stream);
+    c.launches += L.launches;
+    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  });
+}
+
+int vdfgpu_commit_T(const vdfgpu_r1cs* s, vdfgpu_gens* gens, const void* W1_host, const void* u1_host,
+                    const void* X1_host, const void* W2_host, const void* X2_host, void* T_host,
+                    void* comm_T_point96_host) {
+  return guarded([&] {
+    if (!s || !W1_host || !u1_host || !W2_host) throw ArgError("commit_T: null pointer");
+    if (s->io && (!X1_host || !X2_host)) throw ArgError("commit_T: null X");
+    if (gens && !comm_T_point96_host) throw ArgError("commit_T: null commitment output");
+    if (gens) {
+      check_gens_field(s, gens);
+      if (gens->n < s->cons) throw ArgError("commit_T: fewer generators than constraints");
+    }
+    require_ready();
+    Context& c = ctx();
+    CudaLaunch L(c.stream);
+    const size_t nv = s->vars, io = s->io, nc = s->cons;
+    DevBuf<fe> W1(nv ? nv : 1, c.stream), W2(nv ? nv : 1, c.stream), uX1(1 + io, c.stream), uX2(1 + io, c.stream);
+    DevBuf<fe> T(nc, c.stream);
+    DevBuf<jac_t> comm(1, c.stream);
+    h2d(W1.p, W1_host, nv * 32, c.stream);
+    h2d(W2.p, W2_host, nv * 32, c.stream);
+    h2d(uX1.p, u1_host, 32, c.stream);
+    h2d(uX1.p + 1, X1_host, io * 32, c.stream);
+    fe one = host_one(s->field);
+    h2d(uX2.p, &one, 32, c.stream);  // u2 = 1 (fresh instance); pageable 32-byte copy is staged by the driver
+    h2d(uX2.p + 1, X2_host, io * 32, c.stream);
+    launch_cross_term(L, s, ZView{W1.p, uX1.p, uX1.p + 1}, ZView{W2.p, uX2.p, uX2.p + 1}, T.p);
+    c.launches += L.launches;
+    if (gens) {
+      msm_on_device(gens, 0, T.p, nc, comm.p, true);
+      d2h(comm_T_point96_host, comm.p, sizeof(jac_t), c.stream);
+    }
+    if (T_host) d2h(T_host, T.p, nc * 32, c.stream);
+    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  });
+}
+
+int vdfgpu_fold(int field, void* W1_host, const void* W2_host, size_t nW, void* E1_host, const void* T_host,
+                size_t nE, const void* r32_host) {
+  return guarded([&] {
+    if (field != VDFGPU_FP && field != VDFGPU_FQ) throw ArgError("fold: unknown field");
+    if (!r32_host || (nW && (!W1_host || !W2_host)) || (nE && (!E1_host || !T_host))) throw ArgError("fold: null pointer");
+    if (nW + nE == 0) return;
+    require_ready();
+    Context& c = ctx();
+    CudaLaunch L(c.stream);
+    DevBuf<fe> W1(nW ? nW : 1, c.stream), W2(nW ? nW : 1, c.stream), E1(nE ? nE : 1, c.stream), T(nE ? nE : 1, c.stream), r(1, c.stream);
+    h2d(W1.p, W1_host, nW * 32, c.stream);
+    h2d(W2.p, W2_host, nW * 32, c.stream);
+    h2d(E1.p, E1_host, nE * 32, c.stream);
+    h2d(T.p, T_host, nE * 32, c.stream);
+    h2d(r.p, r32_host, 32, c.stream);
+    launch_fold(L, field, W1.p, W2.p, nW, E1.p, T.p, nE, r.p);
+    d2h(W1_host, W1.p, nW * 32, c.stream);
+    d2h(E1_host, E1.p, nE * 32, c.stream);
+    c.launches += L.launches;
+    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  });
+}
+
+// ---- device-resident running instance -------------------------------------------------------------------
+int vdfgpu_running_create(const vdfgpu_r1cs* s, vdfgpu_gens* gens, vdfgpu_running** out) {
+  return guarded([&] {
+    if (!s || !gens || !out) throw ArgError("running_create: null pointer");
+    check_gens_field(s, gens);
+    if (gens->n < s->cons || gens->n < s->vars) throw ArgError("running_create: fewer generators than max(cons, vars)");
+    require_ready();
+    vdfgpu_running* f = new vdfgpu_running();
+    f->shape = s;
+    f->gens = gens;
+    const size_t nv = s->vars ? s->vars : 1, nc = s->cons, io1 = 1 + s->io;
+    try {
+      VDF_CUDA_CHECK(cudaMalloc((void**)&f->W, nv * 32));
+      VDF_CUDA_CHECK(cudaMalloc((void**)&f->W2, nv * 32));
+      VDF_CUDA_CHECK(cudaMalloc((void**)&f->E, nc * 32));
+      VDF_CUDA_CHECK(cudaMalloc((void**)&f->T, nc * 32));
+      VDF_CUDA_CHECK(cudaMalloc((void**)&f->uX, io1 * 32));
+      VDF_CUDA_CHECK(cudaMalloc((void**)&f->uX2, io1 * 32));
+      VDF_CUDA_CHECK(cudaMalloc((void**)&f->r, 32));
+      VDF_CUDA_CHECK(cudaMalloc((void**)&f->comm, 2 * sizeof(jac_t)));
+    } catch (...) {
+      cudaFree(f->W); cudaFree(f->W2); cudaFree(f->E); cudaFree(f->T); cudaFree(f->uX); cudaFree(f->uX2);
+      cudaFree(f->r); cudaFree(f->comm);
+      delete f;
+      throw;
+    }
+    *out = f;
+  });
+}
+
+int vdfgpu_running_destroy(vdfgpu_running* f) {
+  return guarded([&] {
+    if (!f) return;
+    if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+    cudaFree(f->W); cudaFree(f->W2); cudaFree(f->E); cudaFree(f->T); cudaFree(f->uX); cudaFree(f->uX2);
+    cudaFree(f->r); cudaFree(f->comm);
+    delete f;
+  });
+}
+
+int vdfgpu_running_set(vdfgpu_running* f, const void* W_host, const void* E_host, const void* u_host,
+                            const void* X_host) {
+  return guarded([&] {
+    if (!f || !W_host || !E_host || !u_host) throw ArgError("running_set: null pointer");
+    if (f->shape->io && !X_host) throw ArgError("running_set: null X");
+    require_ready();
+    Context& c = ctx();
+    h2d(f->W, W_host, (size_t)f->shape->vars * 32, c.stream);
+    h2d(f->E, E_host, (size_t)f->shape->cons * 32, c.stream);
+    h2d(f->uX, u_host, 32, c.stream);
+    h2d(f->uX + 1, X_host, (size_t)f->shape->io * 32, c.stream);
+    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    f->have_running = true;
+    f->have_fresh = false;
+  });
+}
+
+int vdfgpu_running_get(const vdfgpu_running* f, void* W_host, void* E_host, void* u_host, void* X_host) {
+  return guarded([&] {
+    if (!f) throw ArgError("running_get: null handle");
+    if (!f->have_running) throw StateError("running_get: no running instance set");
+    require_ready();
+    Context& c = ctx();
+    if (W_host) d2h(W_host, f->W, (size_t)f->shape->vars * 32, c.stream);
+    if (E_host) d2h(E_host, f->E, (size_t)f->shape->cons * 32, c.stream);
+    if (u_host) d2h(u_host, f->uX, 32, c.stream);
+    if (X_host) d2h(X_host, f->uX + 1, (size_t)f->shape->io * 32, c.stream);
+    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  });
+}
+
+int vdfgpu_running_commit(vdfgpu_running* f, const void* W2_host, const void* X2_host, void* comm_W2_point96_host,
+                       void* comm_T_point96_host) {
+  return guarded([&] {
+    if (!f || !W2_host || !comm_W2_point96_host || !comm_T_point96_host) throw ArgError("running_commit: null pointer");
+    if (f->shape->io && !X2_host) throw ArgError("running_commit: null X2");
+    if (!f->have_running) throw StateError("running_commit: no running instance set");
+    require_ready();
+    Context& c = ctx();
+    CudaLaunch L(c.stream);
+    const vdfgpu_r1cs* s = f->shape;
+    fe one = host_one(s->field);
+    h2d(f->W2, W2_host, (size_t)s->vars * 32, c.stream);
+    h2d(f->uX2, &one, 32, c.stream);
+    h2d(f->uX2 + 1, X2_host, (size_t)s->io * 32, c.stream);
+    // commit(W2)
+    msm_on_device(f->gens, 0, f->W2, s->vars, f->comm, true);
+    // T and commit(T)
+    launch_cross_term(L, s, ZView{f->W, f->uX, f->uX + 1}, ZView{f->W2, f->uX2, f->uX2 + 1}, f->T);
+    c.launches += L.launches;
+    msm_on_device(f->gens, 0, f->T, s->cons, f->comm + 1, true);
+    d2h(comm_W2_point96_host, f->comm, sizeof(jac_t), c.stream);
+    d2h(comm_T_point96_host, f->comm + 1, sizeof(jac_t), c.stream);
+    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    f->have_fresh = true;
+  });
+}
+
+int vdfgpu_running_finish(vdfgpu_running* f, const void* r32_host) {
+  return guarded([&] {
+    if (!f || !r32_host) throw ArgError("running_finish: null pointer");
+    if (!f->have_fresh) throw StateError("running_finish: fold_commit has not been called for this step");
+    require_ready();
+    Context& c = ctx();
+    CudaLaunch L(c.stream);
+    const vdfgpu_r1cs* s = f->shape;
+    h2d(f->r, r32_host, 32, c.stream);
+    launch_fold(L, s->field, f->W, f->W2, s->vars, f->E, f->T, s->cons, f->r);
+    // u <- u + r*1, X <- X + r*X2: the same kernel over the (1 + io)-element tail
+    launch_fold(L, s->field, f->uX, f->uX2, 1 + (size_t)s->io, nullptr, nullptr, 0, f->r);
+    c.launches += L.launches;
+    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    f->have_fresh = false;
+  });
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,108 @@
+// Library context shared by the C-ABI translation units (api_*.cu).  One process drives one GPU.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/vdfgpu.h"
+#include "launch.cuh"
+#include "msm.cuh"
+
+namespace vdf {
+
+struct ArgError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+struct StateError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+struct Context {
+  std::mutex mu;          // serialises library calls (re-entrant use from several host threads)
+  bool ready = false;
+  int device = -1;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;  // stream in use (own_stream or the caller's)
+  uint64_t launches = 0;
+};
+
+Context& ctx();
+void set_error(const std::string& msg);
+void require_ready();   // throws StateError unless vdfgpu_init succeeded (initialises lazily on device 0)
+
+// RAII device buffer on the context stream (stream-ordered)
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  cudaStream_t s = nullptr;
+  DevBuf() = default;
+  DevBuf(size_t count, cudaStream_t st) : s(st) {
+    void* q = nullptr;
+    VDF_CUDA_CHECK(cudaMallocAsync(&q, count * sizeof(T) + 16, st));
+    p = reinterpret_cast<T*>(q);
+  }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), s(o.s) { o.p = nullptr; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) {
+      release();
+      p = o.p; s = o.s; o.p = nullptr;
+    }
+    return *this;
+  }
+  void release() {
+    if (p) cudaFreeAsync(p, s);
+    p = nullptr;
+  }
+  ~DevBuf() { release(); }
+};
+
+inline void h2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  if (bytes) VDF_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+}
+inline void d2h(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  if (bytes) VDF_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+}
+inline void d2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  if (bytes) VDF_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
+}
+
+// wraps a C-ABI body: locks, maps exceptions to status codes + thread-local message
+template <class Body>
+int guarded(Body body) {
+  try {
+    std::lock_guard<std::mutex> lk(ctx().mu);
+    body();
+    return VDFGPU_OK;
+  } catch (const ArgError& e) {
+    set_error(e.what());
+    return VDFGPU_ERR_ARG;
+  } catch (const StateError& e) {
+    set_error(e.what());
+    return VDFGPU_ERR_STATE;
+  } catch (const std::exception& e) {
+    set_error(e.what());
+    return VDFGPU_ERR_CUDA;
+  }
+}
+
+}  // namespace vdf
+
+// handles ------------------------------------------------------------------------------------------
+struct vdfgpu_gens {
+  int curve = 0;
+  size_t n = 0;            // points per level
+  uint32_t flags = 0;
+  uint32_t c = 0;          // window bits of the table (table mode)
+  uint32_t W = 0;          // levels stored (1 in plain mode)
+  vdf::affine_t* pts = nullptr;  // [W][n]
+};
+
+// internal cross-TU entry: MSM over device scalars into a device point, on the context stream
+namespace vdf {
+void msm_on_device(vdfgpu_gens* g, size_t first, const fe* d_scalars, size_t n, jac_t* d_out, bool is_mont);
+}

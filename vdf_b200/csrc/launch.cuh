@@ -1,0 +1,209 @@
+// Launch policies.  Every kernel in this library is a functor `f(size_t i)` run over a 1-D index
+// space; the pipelines (msm.cuh, r1cs.cuh, minroot.cuh) are templates over a policy L:
+//
+//   CudaLaunch  -- the product: real kernels on a CUDA stream, stream-ordered allocations.
+//   HostLaunch  -- tests/emul only: the SAME functors executed by a CPU loop so the pipeline logic
+//                  (digit recoding, counting sort, segmented bucket accumulation, reduction tree) can
+//                  be checked against the oracle in a container without a GPU.  Never linked into
+//                  libvdfgpu.so.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "field.cuh"
+
+namespace vdf {
+
+// ---- atomics usable from both policies ---------------------------------------------------------
+VDF_HD uint32_t atomic_add_u32(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return atomicAdd(p, v);
+#else
+  uint32_t old = *p;
+  *p = old + v;
+  return old;
+#endif
+}
+
+#if defined(__CUDACC__)
+
+#define VDF_CUDA_CHECK(expr)                                                                      \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(e__));              \
+  } while (0)
+
+template <int BLOCK, class Fn>
+__global__ void __launch_bounds__(BLOCK) functor_kernel(Fn f, size_t n) {
+  size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (i < n) f(i);
+}
+
+// exclusive scan of u32 counters (3 phases); out has n+1 entries, out[n] = total
+template <int BLOCK, int ITEMS>
+__global__ void __launch_bounds__(BLOCK) scan_tile_kernel(const uint32_t* in, uint32_t* out, uint32_t* tile_sums,
+                                                          size_t n) {
+  __shared__ uint32_t warp_tot[BLOCK / 32];
+  const size_t base = ((size_t)blockIdx.x * BLOCK + threadIdx.x) * ITEMS;
+  uint32_t v[ITEMS];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < ITEMS; k++) {
+    v[k] = (base + k < n) ? in[base + k] : 0u;
+    sum += v[k];
+  }
+  // warp inclusive scan of per-thread sums
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t inc = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) warp_tot[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t w = (lane < BLOCK / 32) ? warp_tot[lane] : 0u;
+    uint32_t winc = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t o = __shfl_up_sync(0xffffffffu, winc, d);
+      if (lane >= d) winc += o;
+    }
+    if (lane < BLOCK / 32) warp_tot[lane] = winc - w;  // exclusive warp offsets
+    if (lane == 31) tile_sums[blockIdx.x] = winc;      // tile total (lanes >= BLOCK/32 add 0)
+  }
+  __syncthreads();
+  uint32_t run = warp_tot[wid] + inc - sum;
+#pragma unroll
+  for (int k = 0; k < ITEMS; k++) {
+    if (base + k < n) out[base + k] = run;
+    run += v[k];
+  }
+}
+
+// single block: exclusive scan of tile sums in place, total -> *total_out
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) scan_sums_kernel(uint32_t* tile_sums, size_t ntiles, uint32_t* total_out) {
+  __shared__ uint32_t warp_tot[BLOCK / 32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (size_t base = 0; base < ntiles; base += BLOCK) {
+    size_t i = base + threadIdx.x;
+    uint32_t v = (i < ntiles) ? tile_sums[i] : 0u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t w = (lane < BLOCK / 32) ? warp_tot[lane] : 0u;
+      uint32_t winc = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, winc, d);
+        if (lane >= d) winc += o;
+      }
+      if (lane < BLOCK / 32) warp_tot[lane] = winc - w;
+    }
+    __syncthreads();
+    uint32_t excl = carry + warp_tot[wid] + inc - v;
+    if (i < ntiles) tile_sums[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == BLOCK - 1) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total_out = carry;
+}
+
+template <int BLOCK, int ITEMS>
+__global__ void __launch_bounds__(BLOCK) scan_add_kernel(uint32_t* out, const uint32_t* tile_sums, size_t n) {
+  const size_t base = ((size_t)blockIdx.x * BLOCK + threadIdx.x) * ITEMS;
+  const uint32_t add = tile_sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < ITEMS; k++)
+    if (base + k < n) out[base + k] += add;
+}
+
+struct CudaLaunch {
+  cudaStream_t stream;
+  size_t launches = 0;  // kernels launched through this policy (bench.py reports it)
+
+  explicit CudaLaunch(cudaStream_t s) : stream(s) {}
+
+  template <class T>
+  T* alloc(size_t count) {
+    void* p = nullptr;
+    VDF_CUDA_CHECK(cudaMallocAsync(&p, count * sizeof(T) + 16, stream));
+    return reinterpret_cast<T*>(p);
+  }
+  void free(void* p) {
+    if (p) VDF_CUDA_CHECK(cudaFreeAsync(p, stream));
+  }
+  void zero(void* p, size_t bytes) { VDF_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, stream)); }
+  void fill_ff(void* p, size_t bytes) { VDF_CUDA_CHECK(cudaMemsetAsync(p, 0xff, bytes, stream)); }
+
+  template <int BLOCK = 256, class Fn>
+  void run(size_t n, Fn f) {
+    if (n == 0) return;
+    size_t blocks = (n + BLOCK - 1) / BLOCK;
+    functor_kernel<BLOCK, Fn><<<(unsigned)blocks, BLOCK, 0, stream>>>(f, n);
+    VDF_CUDA_CHECK(cudaGetLastError());
+    launches++;
+  }
+
+  // out[0..n] = exclusive prefix sums of in[0..n), out[n] = total
+  void exclusive_scan(const uint32_t* in, uint32_t* out, size_t n) {
+    constexpr int BLOCK = 256, ITEMS = 8;
+    size_t tiles = (n + (size_t)BLOCK * ITEMS - 1) / ((size_t)BLOCK * ITEMS);
+    if (tiles == 0) tiles = 1;
+    uint32_t* tile_sums = alloc<uint32_t>(tiles);
+    scan_tile_kernel<BLOCK, ITEMS><<<(unsigned)tiles, BLOCK, 0, stream>>>(in, out, tile_sums, n);
+    scan_sums_kernel<256><<<1, 256, 0, stream>>>(tile_sums, tiles, out + n);
+    scan_add_kernel<BLOCK, ITEMS><<<(unsigned)tiles, BLOCK, 0, stream>>>(out, tile_sums, n);
+    VDF_CUDA_CHECK(cudaGetLastError());
+    launches += 3;
+    free(tile_sums);
+  }
+};
+
+#endif  // __CUDACC__
+
+// CPU loop policy: tests/emul only (see header comment)
+struct HostLaunch {
+  size_t launches = 0;
+  template <class T>
+  T* alloc(size_t count) {
+    return reinterpret_cast<T*>(std::malloc(count * sizeof(T) + 16));
+  }
+  void free(void* p) { std::free(p); }
+  void zero(void* p, size_t bytes) { std::memset(p, 0, bytes); }
+  void fill_ff(void* p, size_t bytes) { std::memset(p, 0xff, bytes); }
+  template <int BLOCK = 256, class Fn>
+  void run(size_t n, Fn f) {
+    for (size_t i = 0; i < n; i++) f(i);
+    launches++;
+  }
+  void exclusive_scan(const uint32_t* in, uint32_t* out, size_t n) {
+    uint32_t run = 0;
+    for (size_t i = 0; i < n; i++) {
+      uint32_t v = in[i];
+      out[i] = run;
+      run += v;
+    }
+    out[n] = run;
+    launches += 3;
+  }
+};
+
+}  // namespace vdf

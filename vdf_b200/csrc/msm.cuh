@@ -1,0 +1,601 @@
+// Pippenger multi-scalar multiplication  sum_i s_i * P_i  on Pallas / Vesta.
+//
+// Replaces the CPU MSM behind nova-snark's commit(W) / commit(T): Group::vartime_multiscalar_mul ->
+// pasta_msm::{pallas,vesta} -> mult_pippenger_{pallas,vesta} (reached from
+// the reference at src/nova/proof.rs:342-349).
+//
+// Pipeline (every stage is a functor over a 1-D index space, see launch.cuh):
+//   1 digits     scalar (Montgomery) -> canonical -> signed c-bit digits; one key per (window, point);
+//                histogram of bucket sizes with atomics; zero digits are dropped here.
+//   2 scan       exclusive prefix sum of the histogram -> bucket offsets.
+//   3 scatter    one-pass radix (counting) sort of point references by bucket id.  Order inside a bucket
+//                is arbitrary: the group is commutative and the result is canonicalised at the end.
+//   4 accumulate fixed-size ranges of the sorted list per thread (perfect balance whatever the digit
+//                distribution), XYZZ mixed additions; bucket pieces that straddle a range boundary go
+//                to a record list, complete buckets are stored directly.
+//   5 fixup      segmented reduction of the record list (again range-based, log depth), then owners
+//                fold what is left.
+//   6 reduce     sum_j j*B_j by chunked running sums, recursively on the chunk totals.
+//   7 final      tree sum of the partial results, Horner over windows (plain mode only), normalise to
+//                (x, y, 1) and write a pasta_curves Jacobian point.
+//
+// Two generator layouts:
+//   plain : points P_i only; window w has its own bucket set (NB = W sets).
+//   table : levels 2^(c*w) * P_i precomputed once per generator set (Nova's generators are fixed for the
+//           life of PublicParams, src/nova/proof.rs:232-237); all windows share ONE bucket set, so the
+//           bucket reduction is paid once and there is no window combination.  Costs W x the point
+//           memory -- what 180 GB of HBM is for.
+#pragma once
+#include "curve.cuh"
+#include "launch.cuh"
+
+namespace vdf {
+
+struct MsmPlan {
+  uint32_t n = 0;          // points in this MSM
+  uint32_t c = 0;          // window bits
+  uint32_t W = 0;          // windows = ceil(256 / c)
+  uint32_t B = 0;          // buckets per set = 2^(c-1), digit magnitudes 1..B
+  uint32_t NB = 0;         // bucket sets: W (plain) or 1 (table)
+  uint32_t table = 0;      // 1: points[w * level_stride + i] = 2^(c w) P_i
+  uint64_t level_stride = 0;
+  uint32_t S = 64;         // sorted entries per accumulate thread
+  uint32_t G = 16;         // records per fixup-level thread
+  uint32_t logm = 3;       // bucket-reduction chunk = 2^logm buckets
+  uint32_t is_mont = 1;    // scalars arrive in Montgomery form
+};
+
+constexpr uint32_t KEY_SKIP = 0xffffffffu;
+constexpr uint32_t REC_NONE = 0xffffffffu;
+constexpr uint32_t REC_FIRST = 1u, REC_LAST = 2u;
+
+static inline uint32_t msm_windows(uint32_t c) { return (256 + c - 1) / c; }
+
+// window size heuristic (bits): balances n*W additions against bucket-reduction work
+static inline uint32_t msm_pick_c(size_t n, bool table) {
+  uint32_t lg = 0;
+  while (((size_t)1 << (lg + 1)) <= n) lg++;
+  int c;
+  if (table) c = (int)lg - 1;   // one shared bucket set of 2^(c-1) ~ n/4 buckets: reduction stays ~10 %
+  else c = (int)lg - 6;         // W bucket sets of 2^(c-1) buckets each
+  if (c < 4) c = 4;
+  if (c > 20) c = 20;
+  return (uint32_t)c;
+}
+
+// ---- stage 1: digits + histogram -----------------------------------------------------------------
+template <class SF>  // SF = scalar field
+struct DigitsFn {
+  const fe* scalars;
+  uint32_t* keys;    // [W][n]: bucket_global | sign << 31, or KEY_SKIP
+  uint32_t* count;   // [NB * B]
+  MsmPlan p;
+  VDF_HD void operator()(size_t i) const {
+    fe s = fe_load(scalars + i);
+    if (p.is_mont) s = SF::from_mont(s);
+    uint32_t carry = 0;
+    const uint32_t c = p.c, full = 1u << c;
+    for (uint32_t w = 0; w < p.W; w++) {
+      uint32_t bit = w * c, limb = bit >> 5, sh = bit & 31;
+      uint64_t two = s.v[limb];
+      if (limb + 1 < 8) two |= (uint64_t)s.v[limb + 1] << 32;
+      uint32_t raw = (uint32_t)((two >> sh) & (full - 1)) + carry;
+      uint32_t key;
+      if (raw > p.B) {
+        uint32_t mag = full - raw;  // digit = raw - 2^c = -mag
+        carry = 1;
+        key = mag ? ((mag - 1) | 0x80000000u) : KEY_SKIP;
+      } else {
+        carry = 0;
+        key = raw ? (raw - 1) : KEY_SKIP;
+      }
+      if (key != KEY_SKIP) {
+        uint32_t set = p.table ? 0u : w;
+        uint32_t gb = set * p.B + (key & 0x7fffffffu);
+        atomic_add_u32(count + gb, 1u);
+        key = gb | (key & 0x80000000u);
+      }
+      keys[(size_t)w * p.n + i] = key;
+    }
+  }
+};
+
+// ---- stage 3: scatter (counting sort) --------------------------------------------------------------
+struct ScatterFn {
+  const uint32_t* keys;
+  const uint32_t* offs;
+  uint32_t* fill;
+  uint32_t* sref;
+  MsmPlan p;
+  VDF_HD void operator()(size_t e) const {
+    uint32_t key = keys[e];
+    if (key == KEY_SKIP) return;
+    uint32_t gb = key & 0x7fffffffu;
+    uint32_t w = (uint32_t)(e / p.n), i = (uint32_t)(e - (size_t)w * p.n);
+    uint32_t ref = p.table ? (uint32_t)(w * p.level_stride + i) : i;
+    uint32_t pos = offs[gb] + atomic_add_u32(fill + gb, 1u);
+    sref[pos] = ref | (key & 0x80000000u);
+  }
+};
+
+// ---- stages 4/5: range-based segmented accumulation ---------------------------------------------------
+// A "record" is a partial sum of a bucket that straddles a range boundary.
+struct RecHdr {
+  uint32_t bucket;  // REC_NONE if unused
+  uint32_t flags;   // REC_FIRST: piece starts the bucket; REC_LAST: piece ends it
+};
+
+VDF_HD uint32_t upper_bound_u32(const uint32_t* a, uint32_t n, uint32_t x) {
+  // first index with a[idx] > x
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    uint32_t mid = lo + ((hi - lo) >> 1);
+    if (a[mid] <= x) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+template <class C>
+struct AccumulateFn {
+  const uint32_t* offs;  // [NBK + 1]
+  uint32_t NBK;
+  const uint32_t* sref;
+  const affine_t* pts;
+  xyzz_t* buckets;       // [NBK], zero-initialised
+  RecHdr* rec_hdr;       // [2 * threads]
+  xyzz_t* rec_pt;
+  uint32_t S;
+  VDF_HD void operator()(size_t t) const {
+    rec_hdr[2 * t].bucket = REC_NONE;
+    rec_hdr[2 * t + 1].bucket = REC_NONE;
+    const uint32_t M = offs[NBK];
+    const uint64_t lo64 = (uint64_t)t * S;
+    if (lo64 >= M) return;
+    const uint32_t lo = (uint32_t)lo64;
+    const uint32_t hi = (lo64 + S < M) ? (uint32_t)(lo64 + S) : M;
+    uint32_t b = upper_bound_u32(offs, NBK + 1, lo) - 1;
+    uint32_t pos = lo;
+    while (pos < hi) {
+      const uint32_t bs = offs[b], be = offs[b + 1];
+      const uint32_t seg_end = be < hi ? be : hi;
+      const uint32_t seg_start = pos;
+      xyzz_t acc = C::identity();
+      for (; pos < seg_end; pos++) {
+        uint32_t ref = sref[pos];
+        affine_t pt;
+        const affine_t* src = pts + (ref & 0x7fffffffu);
+        pt.x = fe_load(&src->x);
+        pt.y = fe_load(&src->y);
+        C::madd_signed(acc, pt, (ref >> 31) != 0);
+      }
+      const bool first = seg_start == bs, last = seg_end == be;
+      if (first && last) {
+        buckets[b] = acc;
+      } else {
+        size_t slot = (seg_start == lo) ? 2 * t : 2 * t + 1;
+        rec_hdr[slot].bucket = b;
+        rec_hdr[slot].flags = (first ? REC_FIRST : 0u) | (last ? REC_LAST : 0u);
+        rec_pt[slot] = acc;
+      }
+      if (pos == be) {
+        b++;
+        while (b < NBK && offs[b + 1] == pos) b++;
+      }
+    }
+  }
+};
+
+// One level of the segmented reduction over the record list: thread g folds records
+// [g*G, (g+1)*G) ; runs of equal bucket id collapse; a run that both starts with REC_FIRST and ends
+// with REC_LAST is a finished bucket, otherwise it is re-emitted as a record of the next level.
+template <class C>
+struct RecLevelFn {
+  const RecHdr* in_hdr;
+  const xyzz_t* in_pt;
+  size_t n_in;
+  xyzz_t* buckets;
+  RecHdr* out_hdr;  // [2 * threads]
+  xyzz_t* out_pt;
+  uint32_t G;
+  VDF_HD void operator()(size_t g) const {
+    out_hdr[2 * g].bucket = REC_NONE;
+    out_hdr[2 * g + 1].bucket = REC_NONE;
+    size_t lo = g * G, hi = lo + G < n_in ? lo + G : n_in;
+    uint32_t cur = REC_NONE, flags = 0;
+    xyzz_t acc = C::identity();
+    bool have_head = false;  // first emitted run goes to slot 2g, any later one to 2g+1
+    for (size_t r = lo; r <= hi; r++) {
+      uint32_t b = (r < hi) ? in_hdr[r].bucket : REC_NONE;
+      if (r < hi && b == REC_NONE) continue;
+      if (b != cur || r == hi) {
+        if (cur != REC_NONE) {
+          if ((flags & REC_FIRST) && (flags & REC_LAST)) {
+            buckets[cur] = acc;
+          } else {
+            size_t slot = have_head ? 2 * g + 1 : 2 * g;
+            out_hdr[slot].bucket = cur;
+            out_hdr[slot].flags = flags;
+            out_pt[slot] = acc;
+          }
+          have_head = true;
+        }
+        if (r == hi) break;
+        cur = b;
+        flags = 0;
+        acc = C::identity();
+      }
+      flags |= in_hdr[r].flags;
+      C::add(acc, in_pt[r]);
+    }
+  }
+};
+
+// last level: the owner (record flagged REC_FIRST) folds the following records of its bucket
+template <class C>
+struct RecOwnerFn {
+  const RecHdr* hdr;
+  const xyzz_t* pt;
+  size_t n_rec;
+  xyzz_t* buckets;
+  VDF_HD void operator()(size_t r) const {
+    uint32_t b = hdr[r].bucket;
+    if (b == REC_NONE || !(hdr[r].flags & REC_FIRST)) return;
+    xyzz_t acc = pt[r];
+    if (!(hdr[r].flags & REC_LAST)) {
+      for (size_t q = r + 1; q < n_rec; q++) {
+        if (hdr[q].bucket == REC_NONE) continue;
+        if (hdr[q].bucket != b) break;  // cannot happen: REC_LAST closes the bucket first
+        C::add(acc, pt[q]);
+        if (hdr[q].flags & REC_LAST) break;
+      }
+    }
+    buckets[b] = acc;
+  }
+};
+
+// ---- stage 6: bucket reduction ---------------------------------------------------------------------
+// in: [NB][in_stride] points, first cnt of each row used, element j has weight j+1.
+// Thread (set, t) handles chunk [t*m, min((t+1)*m, cnt)):
+//   S_t = sum of the chunk                          -> next level input (weight t, index t-1)
+//   A_t = sum (j - t*m + 1) * in[j], then * 2^shift -> acat (plain weight-1 sum later)
+template <class C>
+struct ReduceLevelFn {
+  const xyzz_t* in;
+  size_t in_stride;
+  uint32_t cnt, T, logm;
+  xyzz_t* next;        // [NB][T]   (next[set*T + t-1] = S_t for t >= 1)
+  xyzz_t* acat;        // [NB][acat_stride], this level at column acat_off
+  size_t acat_stride, acat_off;
+  uint32_t shift;      // doublings applied to A_t: logm * (level - 1)
+  VDF_HD void operator()(size_t idx) const {
+    uint32_t set = (uint32_t)(idx / T), t = (uint32_t)(idx - (size_t)set * T);
+    uint32_t m = 1u << logm;
+    uint32_t lo = t * m, hi = lo + m < cnt ? lo + m : cnt;
+    const xyzz_t* row = in + (size_t)set * in_stride;
+    xyzz_t run = C::identity(), acc = C::identity();
+    for (uint32_t j = hi; j > lo; j--) {
+      C::add(run, row[j - 1]);
+      C::add(acc, run);
+    }
+    for (uint32_t k = 0; k < shift; k++) acc = C::dbl(acc);
+    acat[(size_t)set * acat_stride + acat_off + t] = acc;
+    if (t >= 1) next[(size_t)set * T + (t - 1)] = run;
+  }
+};
+
+// segmented tree sum: out[set][t] = sum of in[set][t*K .. (t+1)*K)
+template <class C>
+struct SumFn {
+  const xyzz_t* in;
+  size_t in_stride;
+  uint32_t cnt, T, K;
+  xyzz_t* out;
+  size_t out_stride;
+  VDF_HD void operator()(size_t idx) const {
+    uint32_t set = (uint32_t)(idx / T), t = (uint32_t)(idx - (size_t)set * T);
+    uint32_t lo = t * K, hi = lo + K < cnt ? lo + K : cnt;
+    const xyzz_t* row = in + (size_t)set * in_stride;
+    xyzz_t acc = C::identity();
+    for (uint32_t j = lo; j < hi; j++) C::add(acc, row[j]);
+    out[(size_t)set * out_stride + t] = acc;
+  }
+};
+
+// ---- stage 7: final (one thread) -----------------------------------------------------------------------
+template <class C>
+struct FinalFn {
+  const xyzz_t* in;   // [NB][in_stride], cnt used per row
+  size_t in_stride;
+  uint32_t cnt, NB, c;
+  jac_t* out;
+  VDF_HD void operator()(size_t) const {
+    xyzz_t total = C::identity();
+    for (uint32_t s = NB; s > 0; s--) {
+      if (s != NB)
+        for (uint32_t k = 0; k < c; k++) total = C::dbl(total);
+      const xyzz_t* row = in + (size_t)(s - 1) * in_stride;
+      for (uint32_t j = 0; j < cnt; j++) C::add(total, row[j]);
+    }
+    *out = C::to_jac_normalised(total);
+  }
+};
+
+// ---- driver ------------------------------------------------------------------------------------------
+// C = curve (coordinate field), SF = its scalar field.  All pointers are in the policy's memory space.
+template <class L, class C, class SF>
+void msm_run(L& L_, const MsmPlan& p, const affine_t* pts, const fe* scalars, jac_t* out) {
+  const size_t n = p.n, E = n * p.W;
+  const uint32_t NBK = p.NB * p.B;
+  if (n == 0) {
+    L_.zero(out, sizeof(jac_t));
+    return;
+  }
+  uint32_t* keys = L_.template alloc<uint32_t>(E);
+  uint32_t* count = L_.template alloc<uint32_t>(NBK);
+  uint32_t* fill = L_.template alloc<uint32_t>(NBK);
+  uint32_t* offs = L_.template alloc<uint32_t>((size_t)NBK + 1);
+  uint32_t* sref = L_.template alloc<uint32_t>(E);
+  xyzz_t* buckets = L_.template alloc<xyzz_t>(NBK);
+  L_.zero(count, (size_t)NBK * 4);
+  L_.zero(fill, (size_t)NBK * 4);
+  L_.zero(buckets, (size_t)NBK * sizeof(xyzz_t));
+
+  L_.template run<256>(n, DigitsFn<SF>{scalars, keys, count, p});
+  L_.exclusive_scan(count, offs, NBK);
+  L_.template run<256>(E, ScatterFn{keys, offs, fill, sref, p});
+
+  // accumulate over fixed-size ranges of the sorted list
+  size_t T_acc = (E + p.S - 1) / p.S;
+  size_t n_rec = 2 * T_acc;
+  RecHdr* hdr_a = L_.template alloc<RecHdr>(n_rec);
+  xyzz_t* pt_a = L_.template alloc<xyzz_t>(n_rec);
+  L_.template run<128>(T_acc, AccumulateFn<C>{offs, NBK, sref, pts, buckets, hdr_a, pt_a, p.S});
+
+  // segmented reduction of the records: log-depth levels, then owners
+  RecHdr* hdr_b = nullptr;
+  xyzz_t* pt_b = nullptr;
+  const uint32_t G = p.G < 4 ? 4u : p.G;  // each level maps G records to <= 2: needs G > 2 to shrink
+  while (n_rec > 4096) {
+    size_t groups = (n_rec + G - 1) / G;
+    if (!hdr_b) {
+      hdr_b = L_.template alloc<RecHdr>(2 * groups);
+      pt_b = L_.template alloc<xyzz_t>(2 * groups);
+    }
+    L_.template run<128>(groups, RecLevelFn<C>{hdr_a, pt_a, n_rec, buckets, hdr_b, pt_b, G});
+    RecHdr* th = hdr_a; hdr_a = hdr_b; hdr_b = th;
+    xyzz_t* tp = pt_a; pt_a = pt_b; pt_b = tp;
+    n_rec = 2 * groups;
+  }
+  L_.template run<128>(n_rec, RecOwnerFn<C>{hdr_a, pt_a, n_rec, buckets});
+
+  // bucket reduction tree
+  const uint32_t m = 1u << p.logm;
+  // level sizes
+  uint32_t cnts[32], Ts[32];
+  int levels = 0;
+  size_t acat_len = 0;
+  for (uint32_t cnt = p.B;;) {
+    uint32_t T = (cnt + m - 1) / m;
+    cnts[levels] = cnt; Ts[levels] = T;
+    levels++;
+    acat_len += T;
+    if (T <= 1) break;
+    cnt = T - 1;
+  }
+  xyzz_t* acat = L_.template alloc<xyzz_t>((size_t)p.NB * acat_len);
+  xyzz_t* lvl_a = L_.template alloc<xyzz_t>((size_t)p.NB * Ts[0]);
+  xyzz_t* lvl_b = L_.template alloc<xyzz_t>((size_t)p.NB * (levels > 1 ? Ts[1] : 1));
+  {
+    const xyzz_t* in = buckets;
+    size_t in_stride = p.B;
+    size_t off = 0;
+    xyzz_t* nxt = lvl_a;
+    for (int l = 0; l < levels; l++) {
+      L_.template run<128>((size_t)p.NB * Ts[l],
+                           ReduceLevelFn<C>{in, in_stride, cnts[l], Ts[l], p.logm, nxt, acat, acat_len, off,
+                                            p.logm * (uint32_t)l});
+      off += Ts[l];
+      in = nxt;
+      in_stride = Ts[l];
+      nxt = (nxt == lvl_a) ? lvl_b : lvl_a;
+    }
+  }
+  // tree sum of acat rows
+  const uint32_t K = 16;
+  xyzz_t* sum_a = L_.template alloc<xyzz_t>((size_t)p.NB * ((acat_len + K - 1) / K));
+  xyzz_t* sum_b = L_.template alloc<xyzz_t>((size_t)p.NB * ((acat_len + (size_t)K * K - 1) / ((size_t)K * K)));
+  const xyzz_t* cur = acat;
+  size_t cur_stride = acat_len;
+  uint32_t cur_cnt = (uint32_t)acat_len;
+  xyzz_t* dst = sum_a;
+  while (cur_cnt > 32) {
+    uint32_t T = (cur_cnt + K - 1) / K;
+    L_.template run<128>((size_t)p.NB * T, SumFn<C>{cur, cur_stride, cur_cnt, T, K, dst, T});
+    cur = dst;
+    cur_stride = T;
+    cur_cnt = T;
+    dst = (dst == sum_a) ? sum_b : sum_a;
+  }
+  L_.template run<32>(1, FinalFn<C>{cur, cur_stride, cur_cnt, p.NB, p.c, out});
+
+  L_.free(keys); L_.free(count); L_.free(fill); L_.free(offs); L_.free(sref); L_.free(buckets);
+  L_.free(hdr_a); L_.free(pt_a); L_.free(hdr_b); L_.free(pt_b);
+  L_.free(acat); L_.free(lvl_a); L_.free(lvl_b); L_.free(sum_a); L_.free(sum_b);
+}
+
+// ---- generator-set construction ----------------------------------------------------------------------
+// pasta_curves affine (72-byte stride: x, y, infinity:u8 + padding) -> packed 64-byte affine
+struct RepackFn {
+  const uint8_t* src;  // 72-byte stride
+  affine_t* dst;
+  VDF_HD void operator()(size_t i) const {
+    const uint8_t* s = src + i * 72;
+    affine_t a;
+    // 72*i is 8-byte aligned only: read as 64-bit words
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(s);
+    bool inf = s[64] != 0;
+    for (int k = 0; k < 4; k++) {
+      uint64_t xv = inf ? 0 : w[k], yv = inf ? 0 : w[4 + k];
+      a.x.v[2 * k] = (uint32_t)xv; a.x.v[2 * k + 1] = (uint32_t)(xv >> 32);
+      a.y.v[2 * k] = (uint32_t)yv; a.y.v[2 * k + 1] = (uint32_t)(yv >> 32);
+    }
+    fe_store(&dst[i].x, a.x);
+    fe_store(&dst[i].y, a.y);
+  }
+};
+
+struct UnpackFn {  // packed 64-byte affine -> 72-byte pasta_curves affine
+  const affine_t* src;
+  uint8_t* dst;
+  VDF_HD void operator()(size_t i) const {
+    uint8_t* d = dst + i * 72;
+    uint64_t* w = reinterpret_cast<uint64_t*>(d);
+    fe x = fe_load(&src[i].x), y = fe_load(&src[i].y);
+    uint32_t o = 0;
+    for (int k = 0; k < 8; k++) o |= x.v[k] | y.v[k];
+    for (int k = 0; k < 4; k++) {
+      w[k] = (uint64_t)x.v[2 * k] | ((uint64_t)x.v[2 * k + 1] << 32);
+      w[4 + k] = (uint64_t)y.v[2 * k] | ((uint64_t)y.v[2 * k + 1] << 32);
+    }
+    w[8] = (o == 0) ? 1ull : 0ull;  // infinity flag byte + zero padding
+  }
+};
+
+// Table levels: level[l][i] = 2^c * level[l-1][i], produced in XYZZ and normalised with a batched
+// inversion (Montgomery's trick) over chunks of CH points per thread.
+template <class C, class F>
+struct TableLevelFn {
+  const affine_t* prev;
+  affine_t* next;
+  size_t n;
+  uint32_t c;
+  static constexpr int CH = 8;
+  VDF_HD void operator()(size_t t) const {
+    size_t lo = t * CH, hi = lo + CH < n ? lo + CH : n;
+    xyzz_t q[CH];
+    fe pref[CH];
+    fe run = F::one();
+    for (size_t i = lo; i < hi; i++) {
+      affine_t a;
+      a.x = fe_load(&prev[i].x);
+      a.y = fe_load(&prev[i].y);
+      xyzz_t r = C::from_affine(a);
+      for (uint32_t k = 0; k < c; k++) r = C::dbl(r);
+      q[i - lo] = r;
+      pref[i - lo] = run;
+      if (!C::is_inf(r)) run = F::mul(run, F::mul(r.ZZ, r.ZZZ));
+    }
+    fe inv = F::inv(run);
+    for (size_t i = hi; i > lo; i--) {
+      const xyzz_t& r = q[i - 1 - lo];
+      affine_t a;
+      if (C::is_inf(r)) {
+        a.x = F::zero(); a.y = F::zero();
+      } else {
+        fe zi = F::mul(inv, pref[i - 1 - lo]);          // 1 / (ZZ * ZZZ)
+        inv = F::mul(inv, F::mul(r.ZZ, r.ZZZ));
+        a.x = F::mul(r.X, F::mul(zi, r.ZZZ));
+        a.y = F::mul(r.Y, F::mul(zi, r.ZZ));
+      }
+      fe_store(&next[i - 1].x, a.x);
+      fe_store(&next[i - 1].y, a.y);
+    }
+  }
+};
+
+// Synthetic generator sets (bench / tests): P_i = (k0 + i*d) * G with G = (-1, 2), known discrete logs
+// so an MSM of any size can be checked in O(n) scalar-field operations.
+// Setup (one thread): K0 = k0*G, D = d*G (affine), Q = CH*D.  Thread t then emits points
+// [t*CH, (t+1)*CH) starting from K0 + t*Q and stepping by D; chunks are normalised to affine with one
+// batched inversion.
+constexpr int PROG_CH = 16;
+
+struct ProgSetup {
+  xyzz_t K0, Q;
+  fe dx, dy;   // affine D; (0,0) if d == 0
+};
+
+template <class C, class F>
+struct ProgressionSetupFn {
+  fe k0, d;     // canonical (non-Montgomery) 256-bit scalars
+  ProgSetup* out;
+  VDF_HD static xyzz_t mul_gen(const fe& k) {
+    fe gx = F::neg(F::one()), gy = F::dbl(F::one());
+    xyzz_t r = C::identity();
+    for (int limb = 7; limb >= 0; limb--)
+      for (int bit = 31; bit >= 0; bit--) {
+        r = C::dbl(r);
+        if ((k.v[limb] >> bit) & 1u) C::madd(r, gx, gy);
+      }
+    return r;
+  }
+  VDF_HD void operator()(size_t) const {
+    ProgSetup s;
+    s.K0 = mul_gen(k0);
+    xyzz_t D = mul_gen(d);
+    jac_t dj = C::to_jac_normalised(D);
+    s.dx = dj.X;
+    s.dy = dj.Y;
+    if (C::is_inf(D)) { s.dx = F::zero(); s.dy = F::zero(); }
+    xyzz_t q = D;
+    for (int k = 1; k < PROG_CH; k <<= 1) q = C::dbl(q);
+    s.Q = q;
+    *out = s;
+  }
+};
+
+template <class C, class F>
+struct ProgressionFn {
+  const ProgSetup* setup;
+  affine_t* out;
+  size_t n;
+  static constexpr int CH = PROG_CH;
+  VDF_HD void operator()(size_t t) const {
+    size_t lo = t * CH, hi = lo + CH < n ? lo + CH : n;
+    xyzz_t base = C::mul_u32(setup->Q, (uint32_t)t);
+    C::add(base, setup->K0);
+    affine_t D;
+    D.x = setup->dx;
+    D.y = setup->dy;
+    xyzz_t q[CH];
+    fe pref[CH];
+    fe run = F::one();
+    for (size_t i = lo; i < hi; i++) {
+      q[i - lo] = base;
+      pref[i - lo] = run;
+      if (!C::is_inf(base)) run = F::mul(run, F::mul(base.ZZ, base.ZZZ));
+      C::madd_signed(base, D, false);
+    }
+    fe inv = F::inv(run);
+    for (size_t i = hi; i > lo; i--) {
+      const xyzz_t& r = q[i - 1 - lo];
+      affine_t a;
+      if (C::is_inf(r)) {
+        a.x = F::zero(); a.y = F::zero();
+      } else {
+        fe zi = F::mul(inv, pref[i - 1 - lo]);
+        inv = F::mul(inv, F::mul(r.ZZ, r.ZZZ));
+        a.x = F::mul(r.X, F::mul(zi, r.ZZZ));
+        a.y = F::mul(r.Y, F::mul(zi, r.ZZ));
+      }
+      fe_store(&out[i - 1].x, a.x);
+      fe_store(&out[i - 1].y, a.y);
+    }
+  }
+};
+
+// sum of k Jacobian points (multi-GPU partial results): out = normalise(sum)
+template <class C>
+struct JacSumFn {
+  const jac_t* in;
+  uint32_t k;
+  jac_t* out;
+  VDF_HD void operator()(size_t) const {
+    xyzz_t acc = C::identity();
+    for (uint32_t j = 0; j < k; j++) C::add(acc, C::from_jac(in[j]));
+    *out = C::to_jac_normalised(acc);
+  }
+};
+
+}  // namespace vdf

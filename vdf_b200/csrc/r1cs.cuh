@@ -1,0 +1,111 @@
+// Relaxed-R1CS kernels: sparse mat-vec (Az, Bz, Cz), fused folding cross-term T, and the fold update.
+// They replace, inside nova-snark 0.8.0 (called from the reference at src/nova/proof.rs:342-349):
+//   R1CSShape::multiply_vec      -> MultiplyVecFn       
+//   R1CSShape::commit_T (T part) -> CrossTermFn         (row a6;  T = Az1.Bz2 + Az2.Bz1 - u1.Cz2 - u2.Cz1)
+//   RelaxedR1CSWitness::fold     -> FoldFn              (row a7;  W <- W1 + r W2,  E <- E1 + r T)
+//
+// Layout in HBM: the three matrices are stored back to back as ONE CSR with 3*cons rows (A rows, then B,
+// then C): row_ptr u32[3*cons+1], col u32[nnz], val 32-byte Montgomery field elements [nnz].  z is never
+// materialised: column j < vars reads W[j], j == vars reads u, j > vars reads X[j-vars-1], so W stays
+// resident across steps.  All kernels are bound by HBM bandwidth (36 B per non-zero + 32 B per row out).
+#pragma once
+#include "field.cuh"
+#include "launch.cuh"
+
+namespace vdf {
+
+struct CsrView {
+  const uint32_t* row_ptr;  // [3*cons + 1]
+  const uint32_t* col;
+  const fe* val;
+  uint32_t cons, vars, io;
+};
+
+struct ZView {   // z = [W | u | X]
+  const fe* W;
+  const fe* u;   // one element
+  const fe* X;
+};
+
+template <class F>
+VDF_HD fe z_at(const ZView& z, uint32_t vars, uint32_t col) {
+  const fe* p = col < vars ? z.W + col : (col == vars ? z.u : z.X + (col - vars - 1));
+  return fe_load(p);
+}
+
+template <class F>
+VDF_HD fe csr_row_dot(const CsrView& m, uint32_t row, const ZView& z) {
+  fe acc = F::zero();
+  uint32_t lo = m.row_ptr[row], hi = m.row_ptr[row + 1];
+  for (uint32_t k = lo; k < hi; k++) {
+    fe v = fe_load(m.val + k);
+    fe x = z_at<F>(z, m.vars, m.col[k]);
+    acc = F::add(acc, F::mul(v, x));
+  }
+  return acc;
+}
+
+// one thread per (matrix, row): out[mat][row]
+template <class F>
+struct MultiplyVecFn {
+  CsrView m;
+  ZView z;
+  fe* Az; fe* Bz; fe* Cz;
+  VDF_HD void operator()(size_t idx) const {
+    uint32_t row = (uint32_t)idx;
+    fe r = csr_row_dot<F>(m, row, z);
+    uint32_t mat = row / m.cons, rr = row - mat * m.cons;
+    fe* out = mat == 0 ? Az : (mat == 1 ? Bz : Cz);
+    fe_store(out + rr, r);
+  }
+};
+
+// one thread per constraint row: six dot products sharing the row's (col, val) loads, then
+// T = Az1*Bz2 + Az2*Bz1 - u1*Cz2 - Cz1   (u2 = 1 for the fresh instance)
+template <class F>
+struct CrossTermFn {
+  CsrView m;
+  ZView z1, z2;
+  fe* T;
+  VDF_HD void operator()(size_t idx) const {
+    uint32_t row = (uint32_t)idx;
+    fe d1[3], d2[3];
+    for (uint32_t mat = 0; mat < 3; mat++) {
+      fe a1 = F::zero(), a2 = F::zero();
+      uint32_t r = mat * m.cons + row;
+      uint32_t lo = m.row_ptr[r], hi = m.row_ptr[r + 1];
+      for (uint32_t k = lo; k < hi; k++) {
+        fe v = fe_load(m.val + k);
+        uint32_t c = m.col[k];
+        a1 = F::add(a1, F::mul(v, z_at<F>(z1, m.vars, c)));
+        a2 = F::add(a2, F::mul(v, z_at<F>(z2, m.vars, c)));
+      }
+      d1[mat] = a1;
+      d2[mat] = a2;
+    }
+    fe u1 = fe_load(z1.u);
+    fe t = F::add(F::mul(d1[0], d2[1]), F::mul(d2[0], d1[1]));
+    t = F::sub(t, F::mul(u1, d2[2]));
+    t = F::sub(t, d1[2]);
+    fe_store(T + row, t);
+  }
+};
+
+// a[i] <- a[i] + r * b[i] over two vectors in one launch (W with W2, E with T)
+template <class F>
+struct FoldFn {
+  fe* W1; const fe* W2; size_t nW;
+  fe* E1; const fe* T; size_t nE;
+  const fe* r;
+  VDF_HD void operator()(size_t i) const {
+    fe rr = fe_load(r);
+    if (i < nW) {
+      fe_store(W1 + i, F::add(fe_load(W1 + i), F::mul(rr, fe_load(W2 + i))));
+    } else {
+      size_t j = i - nW;
+      fe_store(E1 + j, F::add(fe_load(E1 + j), F::mul(rr, fe_load(T + j))));
+    }
+  }
+};
+
+}  // namespace vdf

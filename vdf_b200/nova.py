@@ -1,0 +1,182 @@
+"""Folding-side host interface: mirror of the nova-snark 0.8 types the reference drives through
+RecursiveSNARK::prove_step (src/nova/proof.rs:342-349): R1CSShape::{multiply_vec, commit_T},
+R1CSWitness::commit, RelaxedR1CS{Witness,Instance}::fold and NIFS::prove.  Vectors live on the GPU; this
+module only marshals bytes and keeps the small instance data (u, X, commitments).
+
+NOT mirrored (out of scope): circuit synthesis (bellperson), the augmented circuit,
+the Poseidon random oracle.  `challenge()` below is a labelled stand-in for the RO so that a chain of
+fold steps can be driven end to end; swap it for nova's RO when binding from Rust.
+"""
+from __future__ import annotations
+
+import ctypes
+import hashlib
+import struct
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+from . import _lib
+from .encoding import (CURVE_BASE, CURVE_ORDER, CURVE_SCALAR_FIELD, MODULUS, POINT_BYTES, Affine,
+                       affine_to_bytes, fe_to_bytes, fes_from_bytes, fes_to_bytes, point_from_bytes)
+from .msm import Generators, mult_pippenger
+
+Coo = List[Tuple[int, int, int]]  # (row, col, value)
+
+
+def _coo_arrays(M: Coo, m: int):
+    rows = struct.pack("<%dQ" % len(M), *[e[0] for e in M])
+    cols = struct.pack("<%dQ" % len(M), *[e[1] for e in M])
+    vals = fes_to_bytes([e[2] for e in M], m)
+    return rows, cols, vals, len(M)
+
+
+class R1CSShape:
+    """nova R1CSShape: A, B, C in COO over z = [W | u | X]; uploaded once as CSR."""
+
+    def __init__(self, field_id: int, num_cons: int, num_vars: int, num_io: int, A: Coo, B: Coo, C: Coo):
+        self.field_id = field_id
+        self.m = MODULUS[field_id]
+        self.num_cons, self.num_vars, self.num_io = num_cons, num_vars, num_io
+        self.nnz = len(A) + len(B) + len(C)
+        a, b, c = (_coo_arrays(M, self.m) for M in (A, B, C))
+        h = ctypes.c_void_p()
+        _lib.check(_lib.load().vdfgpu_r1cs_create(
+            field_id, num_cons, num_vars, num_io,
+            _lib.as_ptr(a[0]), _lib.as_ptr(a[1]), _lib.as_ptr(a[2]), a[3],
+            _lib.as_ptr(b[0]), _lib.as_ptr(b[1]), _lib.as_ptr(b[2]), b[3],
+            _lib.as_ptr(c[0]), _lib.as_ptr(c[1]), _lib.as_ptr(c[2]), c[3], ctypes.byref(h)))
+        self._h = h
+
+    def multiply_vec(self, z: Sequence[int]) -> Tuple[List[int], List[int], List[int]]:
+        if len(z) != self.num_vars + 1 + self.num_io:
+            raise ValueError("z has the wrong length")  # nova: NovaError::InvalidWitnessLength
+        outs = [bytearray(self.num_cons * 32) for _ in range(3)]
+        _lib.check(_lib.load().vdfgpu_multiply_vec(self._h, _lib.as_ptr(fes_to_bytes(z, self.m)),
+                                                   *[_lib.as_ptr(o) for o in outs]))
+        return tuple(fes_from_bytes(bytes(o), self.m) for o in outs)
+
+    def commit_T(self, gens: Optional[Generators], W1: Sequence[int], u1: int, X1: Sequence[int],
+                 W2: Sequence[int], X2: Sequence[int]) -> Tuple[List[int], Affine]:
+        """Cross-term T and its commitment (u2 = 1 for the fresh instance)."""
+        T = bytearray(self.num_cons * 32)
+        comm = bytearray(POINT_BYTES)
+        m = self.m
+        _lib.check(_lib.load().vdfgpu_commit_T(
+            self._h, gens._h if gens else None, _lib.as_ptr(fes_to_bytes(W1, m)), _lib.as_ptr(fe_to_bytes(u1, m)),
+            _lib.as_ptr(fes_to_bytes(X1, m)), _lib.as_ptr(fes_to_bytes(W2, m)), _lib.as_ptr(fes_to_bytes(X2, m)),
+            _lib.as_ptr(T), _lib.as_ptr(comm) if gens else None))
+        cT = point_from_bytes(bytes(comm), CURVE_BASE[gens.curve]) if gens else None
+        return fes_from_bytes(bytes(T), m), cT
+
+    def close(self):
+        if self._h:
+            _lib.load().vdfgpu_r1cs_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def fold_vectors(field_id: int, W1: Sequence[int], W2: Sequence[int], E1: Sequence[int], T: Sequence[int], r: int):
+    """RelaxedR1CSWitness::fold on host vectors: (W1 + r W2, E1 + r T)."""
+    m = MODULUS[field_id]
+    w = bytearray(fes_to_bytes(W1, m))
+    e = bytearray(fes_to_bytes(E1, m))
+    _lib.check(_lib.load().vdfgpu_fold(field_id, _lib.as_ptr(w), _lib.as_ptr(fes_to_bytes(W2, m)), len(W1),
+                                       _lib.as_ptr(e), _lib.as_ptr(fes_to_bytes(T, m)), len(E1),
+                                       _lib.as_ptr(fe_to_bytes(r, m))))
+    return fes_from_bytes(bytes(w), m), fes_from_bytes(bytes(e), m)
+
+
+def point_fold(curve: int, P1: Affine, P2: Affine, r: int) -> Affine:
+    """P1 + r * P2 (RelaxedR1CSInstance::fold's commitment update) as a 2-point MSM on the GPU."""
+    base, order = CURVE_BASE[curve], CURVE_ORDER[curve]
+    pts = affine_to_bytes(P1, base) + affine_to_bytes(P2, base)
+    sc = fe_to_bytes(1, order) + fe_to_bytes(r, order)
+    return point_from_bytes(mult_pippenger(curve, pts, sc, True), base)
+
+
+def challenge(*chunks: bytes) -> int:
+    """STAND-IN for nova's Poseidon random oracle: 128-bit challenge from BLAKE2b of the transcript."""
+    h = hashlib.blake2b(digest_size=16)
+    for c in chunks:
+        h.update(c)
+    return int.from_bytes(h.digest(), "little")
+
+
+@dataclass
+class RelaxedR1CSInstance:  # nova RelaxedR1CSInstance
+    comm_W: Affine
+    comm_E: Affine
+    X: List[int]
+    u: int
+
+
+@dataclass
+class RunningProver:
+    """Device-resident running (W, E) for one curve + the instance on the host: NIFS::prove per step."""
+    shape: R1CSShape
+    gens: Generators
+    U: RelaxedR1CSInstance = None
+    _h: ctypes.c_void_p = field(default_factory=ctypes.c_void_p)
+
+    def __post_init__(self):
+        h = ctypes.c_void_p()
+        _lib.check(_lib.load().vdfgpu_running_create(self.shape._h, self.gens._h, ctypes.byref(h)))
+        self._h = h
+
+    def set_running(self, W: Sequence[int], E: Sequence[int], U: RelaxedR1CSInstance) -> None:
+        m = self.shape.m
+        _lib.check(_lib.load().vdfgpu_running_set(self._h, _lib.as_ptr(fes_to_bytes(W, m)), _lib.as_ptr(fes_to_bytes(E, m)),
+                                                  _lib.as_ptr(fe_to_bytes(U.u, m)), _lib.as_ptr(fes_to_bytes(U.X, m))))
+        self.U = U
+
+    def get_running(self) -> Tuple[List[int], List[int], int, List[int]]:
+        s = self.shape
+        W, E = bytearray(s.num_vars * 32), bytearray(s.num_cons * 32)
+        u, X = bytearray(32), bytearray(max(1, s.num_io) * 32)
+        _lib.check(_lib.load().vdfgpu_running_get(self._h, _lib.as_ptr(W), _lib.as_ptr(E), _lib.as_ptr(u), _lib.as_ptr(X)))
+        m = s.m
+        return (fes_from_bytes(bytes(W), m), fes_from_bytes(bytes(E), m), fes_from_bytes(bytes(u), m)[0],
+                fes_from_bytes(bytes(X[:s.num_io * 32]), m))
+
+    def prove_step_bytes(self, W2: bytes, X2: bytes, r: Optional[int] = None):
+        """One fold of a fresh satisfying (W2, X2): returns (comm_W2, comm_T, r) with points as 96-byte
+        buffers.  Timed region of the fold-steps/s benchmark."""
+        lib = _lib.load()
+        cW, cT = bytearray(POINT_BYTES), bytearray(POINT_BYTES)
+        _lib.check(lib.vdfgpu_running_commit(self._h, _lib.as_ptr(W2), _lib.as_ptr(X2), _lib.as_ptr(cW), _lib.as_ptr(cT)))
+        if r is None:
+            r = challenge(bytes(cW), bytes(cT))
+        _lib.check(lib.vdfgpu_running_finish(self._h, _lib.as_ptr(fe_to_bytes(r, self.shape.m))))
+        return bytes(cW), bytes(cT), r
+
+    def prove_step(self, W2: Sequence[int], X2: Sequence[int], r: Optional[int] = None):
+        """NIFS::prove against the running instance: commit(W2), commit_T, challenge, fold witness and
+        instance.  Returns (comm_T, r)."""
+        m = self.shape.m
+        curve = self.gens.curve
+        base = CURVE_BASE[curve]
+        cW, cT, r = self.prove_step_bytes(fes_to_bytes(W2, m), fes_to_bytes(X2, m), r)
+        comm_W2, comm_T = point_from_bytes(cW, base), point_from_bytes(cT, base)
+        U = self.U
+        self.U = RelaxedR1CSInstance(
+            comm_W=point_fold(curve, U.comm_W, comm_W2, r),
+            comm_E=point_fold(curve, U.comm_E, comm_T, r),
+            X=[(a + r * b) % m for a, b in zip(U.X, X2)],
+            u=(U.u + r) % m)
+        return comm_T, r
+
+    def close(self):
+        if self._h:
+            _lib.load().vdfgpu_running_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
