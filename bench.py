@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path: Pallas MSM Gpoints/s (BASELINE.json metric), with the
+fold-step and batched-verify rates as extra keys on the same JSON line.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--log2n L]
+
+One "step" = one commitment MSM over n = 2^L synthetic scalars against a device-resident generator set
+(P_i = (k0 + i d) G, generated on the device; generators are fixed for the life of PublicParams in the
+reference, src/nova/proof.rs:232-237).  N > 1 (torchrun, one rank per GPU): each rank owns a contiguous point
+range of n points (weak scaling), emits one partial point, and the 96-byte partials are all-gathered (NCCL)
+and summed on every rank -- SURVEY.md section 8(e).
+
+`value`  : device-timed (CUDA events), scalars already in HBM.
+`e2e`    : the same step through the reference-facing C ABI call vdfgpu_msm() with pinned HOST scalars
+           (H2D of n*32 B and D2H of the 96-byte commitment inside the timed region).
+`--impl reference`: the CPU restatement of the reference's pasta-msm Pippenger (oracle/cpu_ref.c, all host
+           cores) on a bounded sample of the same workload; the Rust crates cannot be built here.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "Pallas MSM Gpoints/s"
+K0, D = 0x1234567, 0x89ABCDEF01
+MUL32_PER_FIELD_MUL = 136        # generic CIOS, n = 8 limbs: 2n^2 + n
+FIELD_MUL_PER_MADD = 10          # XYZZ mixed addition 8M + 2S
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2n", type=int, default=22, help="points per GPU = 2^log2n")
+    ap.add_argument("--plain", action="store_true", help="plain generator layout instead of the table")
+    ap.add_argument("--no-extra", action="store_true", help="skip the fold-step / verify side measurements")
+    ap.add_argument("--cpu-log2n", type=int, default=18, help="sample size of the CPU baseline MSM")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def visible_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except (ValueError, IndexError):
+            return local_rank
+    return local_rank
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_msm_baseline(points72: bytes, scalars: bytes, min_seconds: float = 8.0, max_reps: int = 5):
+    """oracle/cpu_ref.c MSM (restatement of pasta-msm's CPU Pippenger) on all host cores."""
+    from oracle import cpu_ref as C
+    cores = C.ncores()
+    n = len(scalars) // 32
+    C.msm(0, points72[:72 * 1024], scalars[:32 * 1024], True, cores)  # warm-up
+    best, total, reps, out = None, 0.0, 0, None
+    while reps < max_reps and (total < min_seconds or reps < 2):
+        t0 = time.perf_counter()
+        out = C.msm(0, points72, scalars, True, cores)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        total += dt
+        reps += 1
+    return {"value": n / best / 1e9, "unit": "Gpoints/s", "cores": cores, "kind": "port",
+            "sample": f"Pallas MSM n=2^{n.bit_length() - 1}, best of {reps} runs, {best * 1e3:.1f} ms each "
+                      f"(oracle/cpu_ref.c: C restatement of pasta-msm's CPU Pippenger; the Rust crates cannot be built here)"}, out
+
+
+def run_reference(args):
+    """CPU arm: the reference algorithm on the host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu_ref as C
+    n = 1 << args.cpu_log2n
+    cores = C.ncores()
+    pts = C.progression(0, K0, D, n)
+    scal = bytearray(os.urandom(32 * n))
+    for i in range(n):
+        scal[32 * i + 31] &= 0x3F
+    scal = bytes(scal)
+    for _ in range(max(1, args.warmup)):
+        C.msm(0, pts, scal, True, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        C.msm(0, pts, scal, True, cores)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = n / dt / 1e9
+    sample = (f"each step = one Pallas MSM over a bounded sample of n=2^{args.cpu_log2n} points of the workload "
+              f"(oracle/cpu_ref.c, C restatement of pasta-msm's CPU Pippenger, {cores} threads)")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Gpoints/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (255-bit Montgomery)", "data": "synthetic",
+            "config": {"workload": f"Pallas MSM, 2^{args.log2n} points per GPU (CPU arm runs a 2^{args.cpu_log2n} sample per step)"},
+            "cpu_baseline": {"value": v, "unit": "Gpoints/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "Gpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def extra_measurements(lib, _lib, torch):
+    """fold-steps/s (t = 1024, synthetic augmented block) and batched verify (C4)."""
+    out = {}
+    from oracle import pasta as O           # builds the synthetic step shape + witness (input generation)
+    from vdf_b200 import msm as G, nova as N
+    try:
+        t, aug = 1024, 9800
+        ovdf = O.PallasVDF()
+        rng = O.XorShiftRng()
+        res = O.State(O.field_random(rng, O.Q), O.field_random(rng, O.Q), t + 5)
+        shape, W, X, _ = O.make_step_instance(O.FIELD_FQ, t, res, aug_cons=aug)
+        gs = N.R1CSShape(O.FIELD_FQ, shape.num_cons, shape.num_vars, shape.num_io, shape.A, shape.B, shape.C)
+        ngen = max(shape.num_cons, shape.num_vars)
+        gens = G.Generators.progression(0, K0, D, ngen, table=True)
+        prover = N.RunningProver(gs, gens)
+        Wb, Xb = O.fes_to_bytes(W, O.Q), O.fes_to_bytes(X, O.Q)
+        prover.set_running(W, [0] * shape.num_cons, N.RelaxedR1CSInstance(None, None, list(X), 1))
+        for _ in range(3):
+            prover.prove_step_bytes(Wb, Xb)
+        reps = 20
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            prover.prove_step_bytes(Wb, Xb)      # H2D witness, MSM(W2), cross-term, MSM(T), D2H, fold
+        dt = (time.perf_counter() - t0) / reps
+        out["nifs_fold"] = {
+            "value": 1.0 / dt, "unit": "NIFS folds/s (one curve: commit(W2) + commit_T + fold, host witness in)",
+            "ms": dt * 1e3, "t": t, "cons": shape.num_cons, "vars": shape.num_vars, "nnz": gs.nnz,
+            "window_bits": gens.window_bits(ngen),
+            "note": "augmented-circuit block is SYNTHETIC (9.8k random constraints); synthesis and the Poseidon RO stay on the host and are not timed"}
+        prover.close(); gens.close(); gs.close()
+    except Exception as e:  # side measurement: never lose the headline line
+        out["nifs_fold"] = {"error": repr(e)}
+    try:
+        n, t = 1 << 16, 1000
+        res = torch.randint(0, 1 << 62, (n, 12), dtype=torch.int64, device="cuda")
+        res[:, 3::4] &= (1 << 61) - 1  # every element < 2^253 < modulus
+        orig = torch.zeros_like(res)
+        ok = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        fn = lib.vdfgpu_minroot_check_batch_dev
+        for _ in range(2):
+            _lib.check(fn(1, res.data_ptr(), orig.data_ptr(), None, t, n, ok.data_ptr()))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        reps = 5
+        for _ in range(reps):
+            _lib.check(fn(1, res.data_ptr(), orig.data_ptr(), None, t, n, ok.data_ptr()))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        steps = n * t
+        out["minroot_verify"] = {"value": steps / (ms * 1e-3), "unit": "MinRoot steps verified/s", "ms": ms,
+                                 "chains": n, "t": t, "mul32_per_step_convention": 3 * MUL32_PER_FIELD_MUL}
+    except Exception as e:
+        out["minroot_verify"] = {"error": repr(e)}
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from vdf_b200 import _lib
+    from vdf_b200 import msm as G
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the GPU path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _lib.load()
+    _lib.check(lib.vdfgpu_init(local_rank))
+    # a dedicated (non-default) torch stream: torch.cuda.Event timing and the library's kernels share it.
+    # (The legacy default stream has handle 0, which vdfgpu_set_stream reads as "use the library stream".)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    _lib.check(lib.vdfgpu_set_stream(stream.cuda_stream))
+
+    n = 1 << args.log2n
+    table = not args.plain
+    steps, warmup = args.steps, max(3, args.warmup)
+
+    # generators: this rank's contiguous point range of the global progression
+    gens = G.Generators.progression(0, K0 + rank * n * D, D, n, table=table)
+    c_bits = gens.window_bits(n)
+    W = (256 + c_bits - 1) // c_bits
+
+    # synthetic scalars: uniform 254-bit values (valid Montgomery-form field elements), seeded per rank
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(42 + rank)
+    scal = torch.randint(-(1 << 63), (1 << 63) - 1, (n, 4), dtype=torch.int64, device="cuda", generator=gen)
+    scal[:, 3] &= (1 << 62) - 1
+    scal_host = torch.empty((n, 4), dtype=torch.int64, pin_memory=True)
+    scal_host.copy_(scal)
+    out_dev = torch.zeros(96, dtype=torch.uint8, device="cuda")
+    gathered = torch.zeros(96 * world, dtype=torch.uint8, device="cuda") if world > 1 else None
+    total_dev = torch.zeros(96, dtype=torch.uint8, device="cuda")
+
+    def step_device():
+        _lib.check(lib.vdfgpu_msm_dev(gens._h, scal.data_ptr(), n, out_dev.data_ptr()))
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out_dev)
+            _lib.check(lib.vdfgpu_point_sum_dev(0, gathered.data_ptr(), world, total_dev.data_ptr()))
+
+    out_host = torch.zeros(96, dtype=torch.uint8, pin_memory=True)
+
+    def step_e2e():
+        # the call a user of the reference makes: commit(scalars) with HOST buffers
+        _lib.check(lib.vdfgpu_msm(gens._h, scal_host.data_ptr(), n, out_host.data_ptr()))
+        if world > 1:
+            out_dev.copy_(out_host, non_blocking=True)
+            dist.all_gather_into_tensor(gathered, out_dev)
+            _lib.check(lib.vdfgpu_point_sum_dev(0, gathered.data_ptr(), world, total_dev.data_ptr()))
+            out_host.copy_(total_dev)
+            torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(visible_index(local_rank))
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.vdfgpu_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        step_device()
+    e1.record()
+    barrier()
+    launches = lib.vdfgpu_launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / steps
+    value = world * n / (ms_per_step * 1e-3) / 1e9
+
+    # end to end through the C ABI with host buffers (wall clock around synchronous calls, max over ranks)
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e = {"value": world * n / e2e_s / 1e9, "unit": "Gpoints/s", "ms_per_step": e2e_s * 1e3,
+           "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 96,
+           "api": "vdfgpu_msm(gens, host scalars, n, host out)"}
+
+    # per-stage device time of the dominant kernel (CUDA events inside the library, same stream)
+    stage_names = ["digits", "scan", "scatter", "accumulate", "records", "reduce", "final"]
+    _lib.check(lib.vdfgpu_profile_enable(1))
+    acc = [0.0] * 7
+    prof_reps = 3
+    for _ in range(prof_reps):
+        _lib.check(lib.vdfgpu_msm_dev(gens._h, scal.data_ptr(), n, out_dev.data_ptr()))
+        buf = (ctypes.c_double * 7)()
+        _lib.check(lib.vdfgpu_profile_read(buf, 7))
+        acc = [a + b for a, b in zip(acc, buf)]
+    _lib.check(lib.vdfgpu_profile_enable(0))
+    stage_ms = {k: v / prof_reps for k, v in zip(stage_names, acc)}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # integer-multiply roofline of the dominant kernel (bucket accumulation)
+    pw, pl, pa = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+    _lib.check(lib.vdfgpu_imad_peak(ctypes.byref(pw), ctypes.byref(pl), ctypes.byref(pa)))
+    alg_mul32 = float(n) * W * FIELD_MUL_PER_MADD * MUL32_PER_FIELD_MUL
+    acc_s = stage_ms["accumulate"] * 1e-3
+    roofline = {
+        "bound": "imad", "kernel": "AccumulateFn (XYZZ bucket accumulation)",
+        "achieved": alg_mul32 / acc_s / 1e12, "peak": pw.value / 1e12, "unit": "Tmul32/s",
+        "frac": (alg_mul32 / acc_s) / pw.value, "traffic": None,
+        "algorithmic": f"n * W(c) * 10 field-mul * 136 mul32 (SURVEY 8d) with the real c={c_bits}, W={W}",
+        "peak_source": "measured in this run: vdfgpu_imad_peak, register-only independent IMAD.WIDE.U32 (32x32+64)",
+        "imad_lo_per_s": pl.value, "iadd3_per_s": pa.value,
+        "kernel_ms": stage_ms["accumulate"], "stage_ms": stage_ms,
+        "share_of_step": stage_ms["accumulate"] / max(1e-9, sum(stage_ms.values())),
+        "judge_convention_c16_achieved": float(n) * 21760 / acc_s / 1e12,
+    }
+
+    cpu_baseline = None
+    parity = None
+    if world == 1:
+        # bounded CPU sample: first 2^cpu_log2n points/scalars of the same workload, and a parity check of
+        # the GPU prefix commitment against it (the only place bench.py executes oracle/)
+        m = min(n, 1 << args.cpu_log2n)
+        pts_bytes = bytearray(72 * m)
+        _lib.check(lib.vdfgpu_gens_export(gens._h, 0, m, _lib.as_ptr(pts_bytes)))
+        sc_bytes = scal_host[:m].numpy().tobytes()
+        cpu_baseline, cpu_out = cpu_msm_baseline(bytes(pts_bytes), sc_bytes)
+        gpu_out = gens.commit_bytes(sc_bytes)
+        parity = "ok" if gpu_out == cpu_out else "MISMATCH"
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "Gpoints/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32 limbs (255-bit Montgomery, exact)", "data": "synthetic",
+        "config": {"workload": f"Pallas MSM (BASELINE config 2/5), n = 2^{args.log2n} points per GPU, "
+                               f"{'table' if table else 'plain'} generator layout, c = {c_bits}, W = {W}",
+                   "points_total": world * n, "scalars": "uniform 254-bit, seed 42+rank",
+                   "points": "known-dlog progression (k0 + i d) G generated on the device",
+                   "l2": "inputs larger than L2 (scalars 32 B/pt + point table 64 B/pt/level >> 126 MB); no flush needed",
+                   "parallelism": f"point-range shards x{world}, all-gather of 96-byte partials" if world > 1 else "single GPU"},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "cpu_baseline": cpu_baseline, "parity_vs_cpu_sample": parity,
+    }
+    if not args.no_extra and world == 1:
+        line["extra"] = extra_measurements(lib, _lib, torch)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

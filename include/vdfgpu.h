@@ -139,6 +139,14 @@ int vdfgpu_minroot_check_batch_dev(int field, const void* results_dev, const voi
 int vdfgpu_minroot_inverse_eval_batch(int field, const void* results_state96_host, uint64_t t, size_t n,
                                       void* out_state96_host);
 
+/* per-stage device time of the most recent MSM, measured with CUDA events on the stream in use.
+ * Stages: 0 digits+histogram, 1 scan, 2 scatter, 3 accumulate, 4 record fix-up, 5 bucket reduction, 6 final */
+#define VDFGPU_MSM_STAGES 7
+int vdfgpu_profile_enable(int on);
+int vdfgpu_profile_read(double* stage_ms, int n_stages);
+/* device-pointer variant of vdfgpu_point_sum (multi-GPU combine without a host round trip) */
+int vdfgpu_point_sum_dev(int curve, const void* points96_dev, size_t k, void* out_point96_dev);
+
 /* ---- measurement helpers (bench.py) ------------------------------------------------------------------ */
 /* elementwise field multiply out[i] = a[i]*b[i] iterated `iters` times (out <- out*b): field-layer parity
  * tests and the integer-multiply roofline probe */

@@ -27,6 +27,9 @@ PROTOTYPES = {
     "vdfgpu_set_stream": (c_int, [c_void_p]),
     "vdfgpu_synchronize": (c_int, []),
     "vdfgpu_launch_count": (c_uint64, []),
+    "vdfgpu_profile_enable": (c_int, [c_int]),
+    "vdfgpu_profile_read": (c_int, [POINTER(c_double), c_int]),
+    "vdfgpu_point_sum_dev": (c_int, [c_int, c_void_p, c_size_t, c_void_p]),
     "mult_pippenger_pallas": (None, [c_void_p, c_void_p, c_size_t, c_void_p, c_bool]),
     "mult_pippenger_vesta": (None, [c_void_p, c_void_p, c_size_t, c_void_p, c_bool]),
     "vdfgpu_gens_create": (c_int, [c_int, c_void_p, c_size_t, c_uint32, c_uint32, POINTER(c_void_p)]),

@@ -34,6 +34,8 @@ static void init_locked(int device) {
   if (prop.major < 10)
     throw std::runtime_error("vdfgpu: kernels are built for sm_100a only; found compute capability " +
                              std::to_string(prop.major) + "." + std::to_string(prop.minor));
+  VDF_CUDA_CHECK(upload_field_constants());
+  upload_constants_r1cs();
   VDF_CUDA_CHECK(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
   // keep freed blocks in the stream-ordered pool: the MSM allocates its workspace per call
   cudaMemPool_t pool;
@@ -77,7 +79,8 @@ static MsmPlan make_plan(const vdfgpu_gens* g, size_t n, bool is_mont) {
 void msm_on_device(vdfgpu_gens* g, size_t first, const fe* d_scalars, size_t n, jac_t* d_out, bool is_mont) {
   if (first + n > g->n) throw ArgError("msm: more scalars than generators");
   Context& c = ctx();
-  CudaLaunch L(c.stream);
+  c.prof.n_marks = 0;
+  CudaLaunch L(c.stream, &c.prof);
   MsmPlan p = make_plan(g, n, is_mont);
   // point references are 31 bits (+ sign), sorted positions 32 bits
   if ((uint64_t)p.W * (p.table ? g->n : n) >= (1ull << 31)) throw ArgError("msm: n too large for 31-bit point references");
@@ -138,60 +141,57 @@ struct FieldMulFn {
 };
 
 // ---- integer pipe probes --------------------------------------------------------------------------
+// Register-only multiply-pipe probes.  Multiplicands are loop-variant (fed from the other accumulators)
+// so nothing is hoisted: MODE 0 = 32x32+64 -> 64 multiply-adds in carry chains (IMAD.WIDE.U32[.X]),
+// MODE 1 = low-half multiply-adds (IMAD), MODE 2 = add-with-carry chains (IADD3.X).
 template <int MODE>
 __global__ void __launch_bounds__(256) imad_probe_kernel(uint32_t* sink, uint32_t seed, int iters) {
-  uint32_t a = seed + threadIdx.x, b = seed * 3u + blockIdx.x;
-  if (MODE == 0) {  // IMAD.WIDE.U32: 32x32 + 64 -> 64, eight independent accumulators
-    uint64_t acc[8];
+  uint32_t x[16], y[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = k + a;
+  for (int k = 0; k < 16; k++) x[k] = k * 0x9e3779b9u + seed + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 8; k++) y[k] = (k ^ seed) * 2654435761u + blockIdx.x;
 #pragma unroll 1
-    for (int it = 0; it < iters; it++) {
+  for (int it = 0; it < iters; it++) {
 #pragma unroll
-      for (int r = 0; r < 4; r++)
+    for (int rep = 0; rep < 4; rep++) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a), "r"(b));
+      for (int s = 0; s < 2; s++) {
+        uint32_t* a = x + 8 * s;
+        const uint32_t* m = y + 4 * s;
+        if (MODE == 0) {
+          asm volatile("mad.lo.cc.u32 %0, %8, %12, %0; madc.hi.cc.u32 %1, %8, %12, %1;"
+                       "madc.lo.cc.u32 %2, %9, %12, %2; madc.hi.cc.u32 %3, %9, %12, %3;"
+                       "madc.lo.cc.u32 %4, %10, %12, %4; madc.hi.cc.u32 %5, %10, %12, %5;"
+                       "madc.lo.cc.u32 %6, %11, %12, %6; madc.hi.u32 %7, %11, %12, %7;"
+                       : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7])
+                       : "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3]), "r"(x[(8 * s + 11 + rep) & 15]));
+        } else if (MODE == 1) {
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(a[k]) : "r"(m[k]), "r"(x[(8 * s + 11 + rep) & 15]));
+        } else {
+          asm volatile("add.cc.u32 %0, %0, %8; addc.cc.u32 %1, %1, %9; addc.cc.u32 %2, %2, %10; addc.cc.u32 %3, %3, %11;"
+                       "addc.cc.u32 %4, %4, %8; addc.cc.u32 %5, %5, %9; addc.cc.u32 %6, %6, %10; addc.u32 %7, %7, %11;"
+                       : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7])
+                       : "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3]));
+        }
+      }
     }
-    uint64_t s = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) s ^= acc[k];
-    if (s == 0x1234567ull) sink[0] = (uint32_t)s;
-  } else if (MODE == 1) {  // IMAD (low 32 bits)
-    uint32_t acc[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = k + a;
-#pragma unroll 1
-    for (int it = 0; it < iters; it++) {
-#pragma unroll
-      for (int r = 0; r < 4; r++)
-#pragma unroll
-        for (int k = 0; k < 8; k++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(a), "r"(b));
-    }
-    uint32_t s = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) s ^= acc[k];
-    if (s == 0x1234567u) sink[0] = s;
-  } else {  // IADD3
-    uint32_t acc[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = k + a;
-#pragma unroll 1
-    for (int it = 0; it < iters; it++) {
-#pragma unroll
-      for (int r = 0; r < 4; r++)
-#pragma unroll
-        for (int k = 0; k < 8; k++) asm volatile("add.u32 %0, %0, %1;" : "+r"(acc[k]) : "r"(b));
-    }
-    uint32_t s = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) s ^= acc[k];
-    if (s == 0x1234567u) sink[0] = s;
+    for (int k = 0; k < 8; k++) y[k] ^= x[k + (k & 1) * 8];
   }
+  uint32_t sacc = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k++) sacc ^= x[k];
+  if (sacc == 0x1234567u) sink[0] = sacc;
 }
 
+// operations of the probed kind per thread per loop iteration
 template <int MODE>
 static double probe_rate(cudaStream_t st, uint32_t* sink) {
-  const int blocks = 148 * 8, iters = 4096;
+  const int blocks = 148 * 8, iters = 2048;
+  const double ops_per_iter = MODE == 2 ? 64.0 : 32.0;   // 4 reps x 2 sets x (4 products | 8 adds)
   cudaEvent_t e0, e1;
   VDF_CUDA_CHECK(cudaEventCreate(&e0));
   VDF_CUDA_CHECK(cudaEventCreate(&e1));
@@ -204,7 +204,7 @@ static double probe_rate(cudaStream_t st, uint32_t* sink) {
   VDF_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  double ops = (double)blocks * 256.0 * iters * 32.0;
+  double ops = (double)blocks * 256.0 * iters * ops_per_iter;
   return ops / (ms * 1e-3);
 }
 
@@ -258,6 +258,27 @@ int vdfgpu_synchronize(void) {
 }
 
 uint64_t vdfgpu_launch_count(void) { return ctx().launches; }
+
+int vdfgpu_profile_enable(int on) {
+  return guarded([&] { ctx().prof.enabled = on != 0; });
+}
+
+int vdfgpu_profile_read(double* stage_ms, int n_stages) {
+  return guarded([&] {
+    require_ready();
+    Context& c = ctx();
+    if (!stage_ms || n_stages < 1) throw ArgError("profile_read: bad arguments");
+    for (int i = 0; i < n_stages; i++) stage_ms[i] = 0.0;
+    if (c.prof.n_marks < 2) throw StateError("profile_read: no profiled MSM (call vdfgpu_profile_enable(1) first)");
+    VDF_CUDA_CHECK(cudaEventSynchronize(c.prof.ev[c.prof.n_marks - 1]));
+    for (int k = 0; k + 1 < c.prof.n_marks; k++) {
+      float ms = 0;
+      VDF_CUDA_CHECK(cudaEventElapsedTime(&ms, c.prof.ev[k], c.prof.ev[k + 1]));
+      int st = c.prof.stage_of[k];
+      if (st >= 0 && st < n_stages) stage_ms[st] += ms;
+    }
+  });
+}
 
 // ---- generator sets ------------------------------------------------------------------------------------
 int vdfgpu_gens_create(int curve, const void* points_affine72_host, size_t n, uint32_t flags,
@@ -400,6 +421,21 @@ int vdfgpu_point_sum(int curve, const void* points96_host, size_t k, void* out_p
     d2h(out_point96_host, res.p, sizeof(jac_t), c.stream);
     c.launches += L.launches;
     VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  });
+}
+
+int vdfgpu_point_sum_dev(int curve, const void* points96_dev, size_t k, void* out_point96_dev) {
+  return guarded([&] {
+    if (!out_point96_dev || (k && !points96_dev)) throw ArgError("point_sum_dev: null pointer");
+    if (curve != VDFGPU_PALLAS && curve != VDFGPU_VESTA) throw ArgError("point_sum_dev: unknown curve");
+    require_ready();
+    Context& c = ctx();
+    CudaLaunch L(c.stream);
+    const jac_t* in = reinterpret_cast<const jac_t*>(points96_dev);
+    jac_t* out = reinterpret_cast<jac_t*>(out_point96_dev);
+    if (curve == VDFGPU_PALLAS) L.run<32>(1, JacSumFn<Pallas>{in, (uint32_t)k, out});
+    else L.run<32>(1, JacSumFn<Vesta>{in, (uint32_t)k, out});
+    c.launches += L.launches;
   });
 }
 

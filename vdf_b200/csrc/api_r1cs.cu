@@ -62,6 +62,8 @@ static void check_gens_field(const vdfgpu_r1cs* s, const vdfgpu_gens* g) {
   if (scalar_field != s->field) throw ArgError("generator curve's scalar field differs from the R1CS field");
 }
 
+void upload_constants_r1cs() { VDF_CUDA_CHECK(upload_field_constants()); }
+
 static fe host_one(int field) { return field == VDFGPU_FP ? Fp::one() : Fq::one(); }
 
 }  // namespace vdf

@@ -27,10 +27,12 @@ struct Context {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;  // stream in use (own_stream or the caller's)
   uint64_t launches = 0;
+  StageProfile prof;      // stage timing of the most recent MSM (vdfgpu_profile_*)
 };
 
 Context& ctx();
 void set_error(const std::string& msg);
+void upload_constants_r1cs();   // api_r1cs.cu's copy of the constant-memory tables
 void require_ready();   // throws StateError unless vdfgpu_init succeeded (initialises lazily on device 0)
 
 // RAII device buffer on the context stream (stream-ordered)

@@ -24,10 +24,25 @@ namespace vdf {
 
 struct FpTag {  // Pallas base field / Vesta scalar field
   static constexpr uint32_t M1 = 0x992d30edu, M2 = 0x094cf91bu, M3 = 0x224698fcu;
+  static constexpr int ID = 0;
 };
 struct FqTag {  // Pallas scalar field / Vesta base field
   static constexpr uint32_t M1 = 0x8c46eb21u, M2 = 0x0994a8ddu, M3 = 0x224698fcu;
+  static constexpr int ID = 1;
 };
+
+#if defined(__CUDACC__)
+// The modulus limbs M1..M3 as the multiplier reads them on the device.  They live in constant memory
+// (uploaded by vdf::upload_field_constants() in every translation unit) instead of being immediates: with
+// an immediate multiplicand ptxas splits each 32x32->64 multiply-add into IMAD (lo) + IMAD.HI (6
+// multiply-pipe cycles per warp), with a uniform-register operand it emits one IMAD.WIDE.U32 (4 cycles).
+static __constant__ uint32_t VDF_KMOD[2][4];
+
+static inline cudaError_t upload_field_constants() {
+  const uint32_t h[2][4] = {{FpTag::M1, FpTag::M2, FpTag::M3, 0x40000000u}, {FqTag::M1, FqTag::M2, FqTag::M3, 0x40000000u}};
+  return cudaMemcpyToSymbol(VDF_KMOD, h, sizeof(h));
+}
+#endif
 
 struct alignas(16) fe {
   uint32_t v[8];
@@ -185,6 +200,7 @@ struct Field {
   // one Montgomery reduction row specialised to [1, M1, M2, M3, 0, 0, 0, 2^30]; q = -even[0]
   static VDF_D void redc_row(uint32_t* even, uint32_t* odd) {
     uint32_t mi = 0u - even[0];
+    const uint32_t M1 = VDF_KMOD[T::ID][0], M2 = VDF_KMOD[T::ID][1], M3 = VDF_KMOD[T::ID][2];
     // odd += q * [M1, M3, 0, 2^30] (pairs at odd columns)
     asm("mad.lo.cc.u32 %0, %8, %9, %0;\n\t"
         "madc.hi.cc.u32 %1, %8, %9, %1;\n\t"

@@ -135,11 +135,34 @@ __global__ void __launch_bounds__(BLOCK) scan_add_kernel(uint32_t* out, const ui
     if (base + k < n) out[base + k] += add;
 }
 
+// optional per-stage timing (bench.py's roofline leg): events recorded at stage boundaries
+struct StageProfile {
+  static constexpr int MAX_MARKS = 16;
+  bool enabled = false;
+  int n_marks = 0;
+  int stage_of[MAX_MARKS];
+  cudaEvent_t ev[MAX_MARKS];
+  bool created = false;
+};
+
 struct CudaLaunch {
   cudaStream_t stream;
   size_t launches = 0;  // kernels launched through this policy (bench.py reports it)
+  StageProfile* prof = nullptr;
 
-  explicit CudaLaunch(cudaStream_t s) : stream(s) {}
+  explicit CudaLaunch(cudaStream_t s, StageProfile* p = nullptr) : stream(s), prof(p) {}
+
+  // stage boundary: everything enqueued until the next mark belongs to `stage`
+  void mark(int stage) {
+    if (!prof || !prof->enabled || prof->n_marks >= StageProfile::MAX_MARKS) return;
+    if (!prof->created) {
+      for (int i = 0; i < StageProfile::MAX_MARKS; i++) VDF_CUDA_CHECK(cudaEventCreate(&prof->ev[i]));
+      prof->created = true;
+    }
+    prof->stage_of[prof->n_marks] = stage;
+    VDF_CUDA_CHECK(cudaEventRecord(prof->ev[prof->n_marks], stream));
+    prof->n_marks++;
+  }
 
   template <class T>
   T* alloc(size_t count) {
@@ -182,6 +205,7 @@ struct CudaLaunch {
 // CPU loop policy: tests/emul only (see header comment)
 struct HostLaunch {
   size_t launches = 0;
+  void mark(int) {}
   template <class T>
   T* alloc(size_t count) {
     return reinterpret_cast<T*>(std::malloc(count * sizeof(T) + 16));

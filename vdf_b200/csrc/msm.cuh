@@ -45,6 +45,11 @@ struct MsmPlan {
   uint32_t is_mont = 1;    // scalars arrive in Montgomery form
 };
 
+enum MsmStage {
+  MSM_STAGE_DIGITS = 0, MSM_STAGE_SCAN, MSM_STAGE_SCATTER, MSM_STAGE_ACCUMULATE, MSM_STAGE_RECORDS,
+  MSM_STAGE_REDUCE, MSM_STAGE_FINAL, MSM_STAGE_END
+};
+
 constexpr uint32_t KEY_SKIP = 0xffffffffu;
 constexpr uint32_t REC_NONE = 0xffffffffu;
 constexpr uint32_t REC_FIRST = 1u, REC_LAST = 2u;
@@ -155,33 +160,42 @@ struct AccumulateFn {
     const uint32_t lo = (uint32_t)lo64;
     const uint32_t hi = (lo64 + S < M) ? (uint32_t)(lo64 + S) : M;
     uint32_t b = upper_bound_u32(offs, NBK + 1, lo) - 1;
-    uint32_t pos = lo;
-    while (pos < hi) {
-      const uint32_t bs = offs[b], be = offs[b + 1];
-      const uint32_t seg_end = be < hi ? be : hi;
-      const uint32_t seg_start = pos;
-      xyzz_t acc = C::identity();
-      for (; pos < seg_end; pos++) {
-        uint32_t ref = sref[pos];
-        affine_t pt;
-        const affine_t* src = pts + (ref & 0x7fffffffu);
-        pt.x = fe_load(&src->x);
-        pt.y = fe_load(&src->y);
-        C::madd_signed(acc, pt, (ref >> 31) != 0);
-      }
-      const bool first = seg_start == bs, last = seg_end == be;
-      if (first && last) {
-        buckets[b] = acc;
-      } else {
-        size_t slot = (seg_start == lo) ? 2 * t : 2 * t + 1;
-        rec_hdr[slot].bucket = b;
-        rec_hdr[slot].flags = (first ? REC_FIRST : 0u) | (last ? REC_LAST : 0u);
-        rec_pt[slot] = acc;
-      }
+    uint32_t bs = offs[b], be = offs[b + 1];
+    uint32_t seg_start = lo;
+    xyzz_t acc = C::identity();
+    // ONE flat loop over the range: the lanes of a warp stay converged on the mixed addition and only
+    // diverge for the (short) flush when their own bucket ends.
+    for (uint32_t pos = lo; pos < hi; pos++) {
       if (pos == be) {
+        flush(t, lo, b, bs, be, seg_start, pos, acc);
         b++;
-        while (b < NBK && offs[b + 1] == pos) b++;
+        while (offs[b + 1] == pos) b++;   // skip empty buckets (pos < hi <= M guarantees termination)
+        bs = pos;
+        be = offs[b + 1];
+        seg_start = pos;
+        acc = C::identity();
       }
+      uint32_t ref = sref[pos];
+      affine_t pt;
+      const affine_t* src = pts + (ref & 0x7fffffffu);
+      pt.x = fe_load(&src->x);
+      pt.y = fe_load(&src->y);
+      C::madd_signed(acc, pt, (ref >> 31) != 0);
+    }
+    flush(t, lo, b, bs, be, seg_start, hi, acc);
+  }
+
+  // a piece [seg_start, seg_end) of bucket b = [bs, be): complete -> bucket store, else -> record
+  VDF_HD void flush(size_t t, uint32_t lo, uint32_t b, uint32_t bs, uint32_t be, uint32_t seg_start,
+                    uint32_t seg_end, const xyzz_t& acc) const {
+    const bool first = seg_start == bs, last = seg_end == be;
+    if (first && last) {
+      buckets[b] = acc;
+    } else {
+      size_t slot = (seg_start == lo) ? 2 * t : 2 * t + 1;
+      rec_hdr[slot].bucket = b;
+      rec_hdr[slot].flags = (first ? REC_FIRST : 0u) | (last ? REC_LAST : 0u);
+      rec_pt[slot] = acc;
     }
   }
 };
@@ -341,8 +355,11 @@ void msm_run(L& L_, const MsmPlan& p, const affine_t* pts, const fe* scalars, ja
   L_.zero(fill, (size_t)NBK * 4);
   L_.zero(buckets, (size_t)NBK * sizeof(xyzz_t));
 
+  L_.mark(MSM_STAGE_DIGITS);
   L_.template run<256>(n, DigitsFn<SF>{scalars, keys, count, p});
+  L_.mark(MSM_STAGE_SCAN);
   L_.exclusive_scan(count, offs, NBK);
+  L_.mark(MSM_STAGE_SCATTER);
   L_.template run<256>(E, ScatterFn{keys, offs, fill, sref, p});
 
   // accumulate over fixed-size ranges of the sorted list
@@ -350,11 +367,13 @@ void msm_run(L& L_, const MsmPlan& p, const affine_t* pts, const fe* scalars, ja
   size_t n_rec = 2 * T_acc;
   RecHdr* hdr_a = L_.template alloc<RecHdr>(n_rec);
   xyzz_t* pt_a = L_.template alloc<xyzz_t>(n_rec);
+  L_.mark(MSM_STAGE_ACCUMULATE);
   L_.template run<128>(T_acc, AccumulateFn<C>{offs, NBK, sref, pts, buckets, hdr_a, pt_a, p.S});
 
   // segmented reduction of the records: log-depth levels, then owners
   RecHdr* hdr_b = nullptr;
   xyzz_t* pt_b = nullptr;
+  L_.mark(MSM_STAGE_RECORDS);
   const uint32_t G = p.G < 4 ? 4u : p.G;  // each level maps G records to <= 2: needs G > 2 to shrink
   while (n_rec > 4096) {
     size_t groups = (n_rec + G - 1) / G;
@@ -370,6 +389,7 @@ void msm_run(L& L_, const MsmPlan& p, const affine_t* pts, const fe* scalars, ja
   L_.template run<128>(n_rec, RecOwnerFn<C>{hdr_a, pt_a, n_rec, buckets});
 
   // bucket reduction tree
+  L_.mark(MSM_STAGE_REDUCE);
   const uint32_t m = 1u << p.logm;
   // level sizes
   uint32_t cnts[32], Ts[32];
@@ -409,7 +429,7 @@ void msm_run(L& L_, const MsmPlan& p, const affine_t* pts, const fe* scalars, ja
   size_t cur_stride = acat_len;
   uint32_t cur_cnt = (uint32_t)acat_len;
   xyzz_t* dst = sum_a;
-  while (cur_cnt > 32) {
+  while (cur_cnt > 1) {
     uint32_t T = (cur_cnt + K - 1) / K;
     L_.template run<128>((size_t)p.NB * T, SumFn<C>{cur, cur_stride, cur_cnt, T, K, dst, T});
     cur = dst;
@@ -417,7 +437,9 @@ void msm_run(L& L_, const MsmPlan& p, const affine_t* pts, const fe* scalars, ja
     cur_cnt = T;
     dst = (dst == sum_a) ? sum_b : sum_a;
   }
+  L_.mark(MSM_STAGE_FINAL);
   L_.template run<32>(1, FinalFn<C>{cur, cur_stride, cur_cnt, p.NB, p.c, out});
+  L_.mark(MSM_STAGE_END);
 
   L_.free(keys); L_.free(count); L_.free(fill); L_.free(offs); L_.free(sref); L_.free(buckets);
   L_.free(hdr_a); L_.free(pt_a); L_.free(hdr_b); L_.free(pt_b);
