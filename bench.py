@@ -348,12 +348,21 @@ def run_ours(args):
     _lib.check(lib.vdfgpu_imad_peak(ctypes.byref(pw), ctypes.byref(pl), ctypes.byref(pa)))
     alg_mul32 = float(n) * W * FIELD_MUL_PER_MADD * MUL32_PER_FIELD_MUL
     acc_s = stage_ms["accumulate"] * 1e-3
+    traffic = None
+    tfile = ROOT / "profiles" / "traffic.json"   # dram bytes of one accumulate launch from the committed ncu capture
+    if tfile.exists():
+        t = json.loads(tfile.read_text())
+        if t.get("log2n") == args.log2n and t.get("window_bits") == c_bits and t.get("layout") == ("table" if table else "plain"):
+            traffic = t["accumulate_dram_bytes_per_launch"]
     roofline = {
         "bound": "imad", "kernel": "AccumulateFn (XYZZ bucket accumulation)",
         "achieved": alg_mul32 / acc_s / 1e12, "peak": pw.value / 1e12, "unit": "Tmul32/s",
-        "frac": (alg_mul32 / acc_s) / pw.value, "traffic": None,
+        "frac": (alg_mul32 / acc_s) / pw.value, "traffic": traffic,
+        "frac_executed": (float(n) * W * FIELD_MUL_PER_MADD * 88 / acc_s) / pw.value,
         "algorithmic": f"n * W(c) * 10 field-mul * 136 mul32 (SURVEY 8d) with the real c={c_bits}, W={W}",
-        "peak_source": "measured in this run: vdfgpu_imad_peak, register-only independent IMAD.WIDE.U32 (32x32+64)",
+        "peak_source": "measured in this run: vdfgpu_imad_peak, register-only IMAD.WIDE.U32.X carry chains with loop-variant "
+                       "multiplicands (nominal 148 SM x 4 SMSP x 8 lanes x 1.965 GHz = 9.3 T; MEASURED_PEAKS.json has no integer figure)",
+        "frac_executed_note": "the specialised multiplier executes 88 products per field multiplication, the SURVEY convention counts 136",
         "imad_lo_per_s": pl.value, "iadd3_per_s": pa.value,
         "kernel_ms": stage_ms["accumulate"], "stage_ms": stage_ms,
         "share_of_step": stage_ms["accumulate"] / max(1e-9, sum(stage_ms.values())),
