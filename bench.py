@@ -32,6 +32,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 METRIC = "Pallas MSM Gpoints/s"
+print_json = print
 K0, D = 0x1234567, 0x89ABCDEF01
 MUL32_PER_FIELD_MUL = 136        # generic CIOS, n = 8 limbs: 2n^2 + n
 FIELD_MUL_PER_MADD = 10          # XYZZ mixed addition 8M + 2S
@@ -153,7 +154,7 @@ def run_reference(args):
             "config": {"workload": f"Pallas MSM, 2^{args.log2n} points per GPU (CPU arm runs a 2^{args.cpu_log2n} sample per step)"},
             "cpu_baseline": {"value": v, "unit": "Gpoints/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "Gpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print_json(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -397,7 +398,7 @@ def run_ours(args):
     }
     if not args.no_extra and world == 1:
         line["extra"] = extra_measurements(lib, _lib, torch)
-    print(json.dumps(line), flush=True)
+    print_json(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -405,10 +406,29 @@ def run_ours(args):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # Exactly ONE line on stdout: libraries (NCCL's version banner, torchrun notices) write to fd 1 too, so
+    # route fd 1 to stderr for the duration of the run and emit the JSON line on the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    captured = []
+
+    def emit(line):
+        captured.append(line)
+
+    global print_json
+    print_json = emit
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        for line in captured:
+            os.write(1, (line + "\n").encode())
+        os.close(real_stdout)
 
 
 if __name__ == "__main__":

@@ -73,6 +73,8 @@ static MsmPlan make_plan(const vdfgpu_gens* g, size_t n, bool is_mont) {
   if (const char* s = std::getenv("VDFGPU_MSM_S")) p.S = (uint32_t)std::atoi(s);
   p.G = 16;
   p.logm = 3;
+  if (const char* s = std::getenv("VDFGPU_MSM_G")) p.G = (uint32_t)std::atoi(s);
+  if (const char* s = std::getenv("VDFGPU_MSM_LOGM")) p.logm = (uint32_t)std::atoi(s);
   return p;
 }
 

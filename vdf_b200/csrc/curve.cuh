@@ -98,11 +98,50 @@ struct Curve {
     acc.Y = Y3;
   }
 
+  // the doubling branch of a mixed addition is taken only when a bucket meets its own point again: keep it
+  // out of the hot kernel's instruction stream
+#if defined(__CUDACC__)
+  static __device__ __noinline__ xyzz_t dbl_affine_cold(const fe& x, const fe& y) { return dbl_affine(x, y); }
+#else
+  static xyzz_t dbl_affine_cold(const fe& x, const fe& y) { return dbl_affine(x, y); }
+#endif
+
+  // madd with the multiplier called out of line (same arithmetic; used by the accumulate kernel)
+  static VDF_HD void madd_call(xyzz_t& acc, const fe& x2, const fe& y2) {
+    if (is_inf(acc)) {
+      acc.X = x2; acc.Y = y2; acc.ZZ = F::one(); acc.ZZZ = F::one();
+      return;
+    }
+    fe U2 = F::mul_call(x2, acc.ZZ);
+    fe S2 = F::mul_call(y2, acc.ZZZ);
+    fe P = F::sub(U2, acc.X);
+    fe R = F::sub(S2, acc.Y);
+    if (F::is_zero(P)) {
+      if (F::is_zero(R)) acc = dbl_affine_cold(x2, y2);
+      else acc = identity();
+      return;
+    }
+    fe PP = F::mul_call(P, P);
+    fe PPP = F::mul_call(P, PP);
+    fe Q = F::mul_call(acc.X, PP);
+    fe X3 = F::sub(F::sub(F::mul_call(R, R), PPP), F::dbl(Q));
+    fe Y3 = F::sub(F::mul_call(R, F::sub(Q, X3)), F::mul_call(acc.Y, PPP));
+    acc.ZZ = F::mul_call(acc.ZZ, PP);
+    acc.ZZZ = F::mul_call(acc.ZZZ, PPP);
+    acc.X = X3;
+    acc.Y = Y3;
+  }
+
   // acc += sign ? -(p) : p for a packed affine point (identity allowed)
   static VDF_HD void madd_signed(xyzz_t& acc, const affine_t& p, bool negate) {
     if (aff_is_inf(p)) return;
     fe y = negate ? F::neg(p.y) : p.y;
     madd(acc, p.x, y);
+  }
+  static VDF_HD void madd_signed_call(xyzz_t& acc, const affine_t& p, bool negate) {
+    if (aff_is_inf(p)) return;
+    fe y = negate ? F::neg(p.y) : p.y;
+    madd_call(acc, p.x, y);
   }
 
   // acc += q (add-2008-s), all special cases handled

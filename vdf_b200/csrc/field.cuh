@@ -367,6 +367,14 @@ struct Field {
 
   static VDF_HD fe sqr(const fe& a) { return mul(a, a); }
 
+  // Out-of-line copy for kernels whose fully inlined body would overflow the instruction cache (the bucket
+  // accumulation inlines ~20 multiplications): one shared 250-instruction body instead.
+#if defined(__CUDACC__)
+  static __device__ __noinline__ fe mul_call(const fe& a, const fe& b) { return mul(a, b); }
+#else
+  static fe mul_call(const fe& a, const fe& b) { return mul(a, b); }
+#endif
+
   // Montgomery -> canonical: multiply by the integer 1
   static VDF_HD fe from_mont(const fe& a) {
     fe o = zero();

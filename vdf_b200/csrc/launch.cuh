@@ -38,8 +38,11 @@ VDF_HD uint32_t atomic_add_u32(uint32_t* p, uint32_t v) {
       throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(e__));              \
   } while (0)
 
+#ifndef VDF_MIN_BLOCKS
+#define VDF_MIN_BLOCKS 1
+#endif
 template <int BLOCK, class Fn>
-__global__ void __launch_bounds__(BLOCK) functor_kernel(Fn f, size_t n) {
+__global__ void __launch_bounds__(BLOCK, VDF_MIN_BLOCKS) functor_kernel(Fn f, size_t n) {
   size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
   if (i < n) f(i);
 }

@@ -180,7 +180,7 @@ struct AccumulateFn {
       const affine_t* src = pts + (ref & 0x7fffffffu);
       pt.x = fe_load(&src->x);
       pt.y = fe_load(&src->y);
-      C::madd_signed(acc, pt, (ref >> 31) != 0);
+      C::madd_signed_call(acc, pt, (ref >> 31) != 0);
     }
     flush(t, lo, b, bs, be, seg_start, hi, acc);
   }
