@@ -85,6 +85,10 @@ int vdfgpu_gens_destroy(vdfgpu_gens* g);
 /* commit(v) = sum_i v_i * gens[i] over the first n generators; scalars in Montgomery form */
 int vdfgpu_msm(vdfgpu_gens* g, const void* scalars32_host, size_t n, void* out_point96_host);
 int vdfgpu_msm_dev(vdfgpu_gens* g, const void* scalars32_dev, size_t n, void* out_point96_dev);
+/* k <= 4 scalar vectors (lengths lens[j]) over the same generators in ONE pass: k commitments for the latency
+ * of one MSM.  nova commits to W and T of one NIFS::prove with the same generators. */
+int vdfgpu_msm_batch_dev(vdfgpu_gens* g, const void* const* scalars32_dev, const size_t* lens, uint32_t k,
+                         void* out_points96_dev);
 /* point range [first, first+n) of the set: the shard a rank owns in the multi-GPU MSM */
 int vdfgpu_msm_range_dev(vdfgpu_gens* g, size_t first, const void* scalars32_dev, size_t n,
                          void* out_point96_dev);

@@ -48,6 +48,8 @@ MsmPlan plan_for(size_t n, size_t stride, int table, uint32_t c, uint32_t S, uin
   p.G = G;
   p.logm = logm;
   p.is_mont = is_mont ? 1u : 0u;
+  p.batch = 1;
+  p.len[0] = (uint32_t)n;
   return p;
 }
 
@@ -78,9 +80,39 @@ int emul_msm(int curve, int table, uint32_t c, uint32_t S, uint32_t G, uint32_t 
   std::vector<fe> sc(n ? n : 1);
   std::memcpy(sc.data(), scalars, n * 32);
   jac_t out;
-  if (curve == 0) msm_run<HostLaunch, Pallas, Fq>(L, p, pts.data(), sc.data(), &out);
-  else msm_run<HostLaunch, Vesta, Fp>(L, p, pts.data(), sc.data(), &out);
+  ScalarSet ss{{sc.data(), nullptr, nullptr, nullptr}};
+  if (curve == 0) msm_run<HostLaunch, Pallas, Fq>(L, p, pts.data(), ss, &out);
+  else msm_run<HostLaunch, Vesta, Fp>(L, p, pts.data(), ss, &out);
   std::memcpy(out96, &out, 96);
+  return 0;
+}
+
+// batched MSM: k scalar vectors (lengths lens[j] <= n, concatenated in `scalars`) over the same n points
+int emul_msm_batch(int curve, int table, uint32_t c, uint32_t S, const void* affine72, size_t n, const void* scalars,
+                   const uint32_t* lens, uint32_t k, void* out96k) {
+  HostLaunch L;
+  uint32_t W = table ? msm_windows(c) : 1;
+  std::vector<affine_t> pts((size_t)W * (n ? n : 1));
+  L.run(n, RepackFn{(const uint8_t*)affine72, pts.data()});
+  if (table)
+    for (uint32_t l = 1; l < W; l++) {
+      size_t threads = (n + 7) / 8;
+      if (curve == 0) L.run(threads, TableLevelFn<Pallas, Fp>{pts.data() + (size_t)(l - 1) * n, pts.data() + (size_t)l * n, n, c});
+      else L.run(threads, TableLevelFn<Vesta, Fq>{pts.data() + (size_t)(l - 1) * n, pts.data() + (size_t)l * n, n, c});
+    }
+  MsmPlan p = plan_for(n, n, table, c, S, 4, 2, 1);
+  p.batch = k;
+  size_t total = 0;
+  for (uint32_t j = 0; j < k; j++) total += lens[j];
+  std::vector<fe> sc(total + 1);
+  std::memcpy(sc.data(), scalars, total * 32);
+  ScalarSet ss{{nullptr, nullptr, nullptr, nullptr}};
+  size_t off = 0;
+  for (uint32_t j = 0; j < k; j++) { ss.v[j] = sc.data() + off; p.len[j] = lens[j]; off += lens[j]; }
+  std::vector<jac_t> out(k);
+  if (curve == 0) msm_run<HostLaunch, Pallas, Fq>(L, p, pts.data(), ss, out.data());
+  else msm_run<HostLaunch, Vesta, Fp>(L, p, pts.data(), ss, out.data());
+  std::memcpy(out96k, out.data(), 96 * (size_t)k);
   return 0;
 }
 

@@ -66,7 +66,12 @@ def test_msm_pipeline(emul, cid, table):
     pts[9], sc[9] = pts[8], sc[8]
     pts[11], sc[11] = cv.neg(pts[10]), sc[10]
     want = O.jac_to_bytes(cv, cv.msm(sc, pts))
-    for c, S, G, logm in ((4, 5, 4, 1), (7, 16, 4, 2), (8, 64, 16, 3), (11, 33, 16, 3), (13, 7, 5, 3)):
+    # stage 6 has three paths: c <= 3 the recursive running-sum tree, 4 <= c <= 16 the bit decomposition,
+    # c >= 17 the hybrid (one running-sum level, then bit decomposition); logm = 5 at c = 17 forces the tree
+    for c, S, G, logm in ((2, 9, 4, 1), (3, 5, 4, 2), (4, 5, 4, 1), (7, 16, 4, 2), (8, 64, 16, 3), (11, 33, 16, 3),
+                          (13, 7, 5, 3), (16, 50, 16, 2), (17, 64, 16, 3), (18, 64, 16, 2), (17, 64, 16, 14)):
+        if c >= 15 and not table:
+            continue  # W bucket sets of 2^14+ buckets: too slow for the CPU loop; the table layout covers the path
         assert _msm(emul, cid, table, c, S, G, logm, pts, sc) == want, (c, S, G, logm)
     assert _msm(emul, cid, table, 8, 16, 4, 3, pts, sc, is_mont=0) == want
 
@@ -156,3 +161,22 @@ def test_r1cs_cross_term_and_fold(emul, fid):
     emul.emul_fold(fid, ptr(w1), ptr(w2), SZ(len(W1)), ptr(e1), ptr(tb), SZ(len(E1)), ptr(aligned(O.fe_to_bytes(r, m))))
     assert O.fes_from_bytes(w1.tobytes(), m) == O.fold_vec(W1, W2, r, m)
     assert O.fes_from_bytes(e1.tobytes(), m) == O.fold_vec(E1, T, r, m)
+
+
+@pytest.mark.parametrize("table", [0, 1])
+def test_msm_batch(emul, table):
+    """k scalar vectors of different lengths over the same generators in one pass (commit(W2), commit(T))."""
+    cv = O.PALLAS
+    rng, py = O.XorShiftRng(), random.Random(9)
+    n = 150
+    pts = cv.progression(8, 3, n)
+    vecs = [rand_scalars(rng, cv.order, 150), nova_like_scalars(py, rng, cv.order, 97), [], [5]]
+    for k in (1, 2, 4):
+        use = vecs[:k]
+        lens = np.array([len(v) for v in use], dtype=np.uint32)
+        sb = aligned(b"".join(O.fes_to_bytes(v, cv.order) for v in use))
+        out = np.zeros(96 * k, np.uint8)
+        assert emul.emul_msm_batch(0, table, 7, 9, ptr(aligned(O.affines_to_bytes(cv, pts))), SZ(n), ptr(sb),
+                                   ptr(lens), k, ptr(out)) == 0
+        for j, v in enumerate(use):
+            assert out.tobytes()[96 * j:96 * j + 96] == O.jac_to_bytes(cv, cv.msm_known_dlog(v, 8, 3)), (k, j)

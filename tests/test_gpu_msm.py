@@ -121,3 +121,27 @@ def test_msm_argument_errors(gpu_lib):
         g.commit_bytes(bytes(32 * 17))  # more scalars than generators
     with pytest.raises(VdfGpuError):
         G.Generators.from_affine_bytes(0, b"", table=False)
+
+
+def test_msm_batch_dev(gpu_lib):
+    """vdfgpu_msm_batch_dev: three scalar vectors of different lengths, one pass, device pointers."""
+    import ctypes
+
+    import torch
+
+    from vdf_b200 import _lib
+    cv = O.PALLAS
+    rng, py = O.XorShiftRng(), random.Random(4)
+    n, k0, d = 5000, 17, 29
+    g = G.Generators.progression(cv.cid, k0, d, n, table=True)
+    vecs = [rand_scalars(rng, cv.order, 5000), nova_like_scalars(py, rng, cv.order, 3777), [7]]
+    dev = [torch.frombuffer(bytearray(O.fes_to_bytes(v, cv.order)), dtype=torch.uint8).cuda() for v in vecs]
+    ptrs = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in dev])
+    lens = (ctypes.c_size_t * 3)(*[len(v) for v in vecs])
+    out = torch.zeros(96 * 3, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    _lib.check(gpu_lib.vdfgpu_msm_batch_dev(g._h, ptrs, lens, 3, out.data_ptr()))
+    _lib.check(gpu_lib.vdfgpu_synchronize())
+    raw = out.cpu().numpy().tobytes()
+    for j, v in enumerate(vecs):
+        assert O.jac_from_bytes(cv, raw[96 * j:96 * j + 96]) == cv.msm_known_dlog(v, k0, d)

@@ -40,6 +40,7 @@ PROTOTYPES = {
     "vdfgpu_gens_destroy": (c_int, [c_void_p]),
     "vdfgpu_msm": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "vdfgpu_msm_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vdfgpu_msm_batch_dev": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_size_t), c_uint32, c_void_p]),
     "vdfgpu_msm_range_dev": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
     "vdfgpu_point_sum": (c_int, [c_int, c_void_p, c_size_t, c_void_p]),
     "vdfgpu_r1cs_create": (c_int, [c_int, c_size_t, c_size_t, c_size_t,

@@ -53,9 +53,11 @@ void require_ready() {
 }
 
 // ---- MSM dispatch -----------------------------------------------------------------------------------
-static MsmPlan make_plan(const vdfgpu_gens* g, size_t n, bool is_mont) {
+static MsmPlan make_plan(const vdfgpu_gens* g, size_t n, bool is_mont, uint32_t batch = 1) {
   MsmPlan p;
   p.n = (uint32_t)n;
+  p.batch = batch;
+  for (uint32_t j = 0; j < MSM_MAX_BATCH; j++) p.len[j] = j < batch ? (uint32_t)n : 0u;
   p.table = (g->flags & VDFGPU_GENS_TABLE) ? 1u : 0u;
   p.c = p.table ? g->c : msm_pick_c(n, false);
   p.W = msm_windows(p.c);
@@ -65,9 +67,10 @@ static MsmPlan make_plan(const vdfgpu_gens* g, size_t n, bool is_mont) {
   p.is_mont = is_mont ? 1u : 0u;
   // entries per accumulate thread: enough threads to fill 148 SMs, ranges long enough to amortise
   // the two boundary records each thread may emit
-  size_t E = n * p.W;
+  size_t E = n * p.W * batch;
   size_t S = E / (148 * 768);
-  if (S < 32) S = 32;
+  const size_t s_min = E <= (1u << 21) ? 16 : 32;   // latency path: shorter serial chains per thread
+  if (S < s_min) S = s_min;
   if (S > 128) S = 128;
   p.S = (uint32_t)S;
   if (const char* s = std::getenv("VDFGPU_MSM_S")) p.S = (uint32_t)std::atoi(s);
@@ -87,8 +90,34 @@ void msm_on_device(vdfgpu_gens* g, size_t first, const fe* d_scalars, size_t n, 
   // point references are 31 bits (+ sign), sorted positions 32 bits
   if ((uint64_t)p.W * (p.table ? g->n : n) >= (1ull << 31)) throw ArgError("msm: n too large for 31-bit point references");
   const affine_t* pts = g->pts + first;
-  if (g->curve == VDFGPU_PALLAS) msm_run<CudaLaunch, Pallas, Fq>(L, p, pts, d_scalars, d_out);
-  else msm_run<CudaLaunch, Vesta, Fp>(L, p, pts, d_scalars, d_out);
+  ScalarSet ss{{d_scalars, nullptr, nullptr, nullptr}};
+  if (g->curve == VDFGPU_PALLAS) msm_run<CudaLaunch, Pallas, Fq>(L, p, pts, ss, d_out);
+  else msm_run<CudaLaunch, Vesta, Fp>(L, p, pts, ss, d_out);
+  c.launches += L.launches;
+}
+
+// k scalar vectors over the same generators in ONE pass of the pipeline (one bucket set per vector):
+// the latency of one MSM for k commitments.  d_out receives k points.
+void msm_batch_on_device(vdfgpu_gens* g, const fe* const* d_scalars, const size_t* lens, uint32_t k, jac_t* d_out) {
+  if (k == 0 || k > MSM_MAX_BATCH) throw ArgError("msm_batch: batch size must be 1..4");
+  size_t n = 0;
+  for (uint32_t j = 0; j < k; j++) {
+    if (lens[j] > g->n) throw ArgError("msm_batch: more scalars than generators");
+    if (lens[j] > n) n = lens[j];
+  }
+  Context& c = ctx();
+  c.prof.n_marks = 0;
+  CudaLaunch L(c.stream, &c.prof);
+  MsmPlan p = make_plan(g, n, true, k);
+  if ((uint64_t)p.W * (p.table ? g->n : n) >= (1ull << 31) || (uint64_t)p.W * n * k >= (1ull << 32))
+    throw ArgError("msm_batch: too large");
+  ScalarSet ss{{nullptr, nullptr, nullptr, nullptr}};
+  for (uint32_t j = 0; j < k; j++) {
+    ss.v[j] = d_scalars[j];
+    p.len[j] = (uint32_t)lens[j];
+  }
+  if (g->curve == VDFGPU_PALLAS) msm_run<CudaLaunch, Pallas, Fq>(L, p, g->pts, ss, d_out);
+  else msm_run<CudaLaunch, Vesta, Fp>(L, p, g->pts, ss, d_out);
   c.launches += L.launches;
 }
 
@@ -393,6 +422,16 @@ int vdfgpu_msm_dev(vdfgpu_gens* g, const void* scalars32_dev, size_t n, void* ou
     require_ready();
     msm_on_device(g, 0, reinterpret_cast<const fe*>(scalars32_dev), n, reinterpret_cast<jac_t*>(out_point96_dev),
                   true);
+  });
+}
+
+int vdfgpu_msm_batch_dev(vdfgpu_gens* g, const void* const* scalars32_dev, const size_t* lens, uint32_t k,
+                         void* out_points96_dev) {
+  return guarded([&] {
+    if (!g || !scalars32_dev || !lens || !out_points96_dev) throw ArgError("msm_batch_dev: null pointer");
+    require_ready();
+    msm_batch_on_device(g, reinterpret_cast<const fe* const*>(scalars32_dev), lens, k,
+                        reinterpret_cast<jac_t*>(out_points96_dev));
   });
 }
 

@@ -296,12 +296,12 @@ int vdfgpu_running_commit(vdfgpu_running* f, const void* W2_host, const void* X2
     h2d(f->W2, W2_host, (size_t)s->vars * 32, c.stream);
     h2d(f->uX2, &one, 32, c.stream);
     h2d(f->uX2 + 1, X2_host, (size_t)s->io * 32, c.stream);
-    // commit(W2)
-    msm_on_device(f->gens, 0, f->W2, s->vars, f->comm, true);
-    // T and commit(T)
+    // T, then commit(W2) and commit(T) in one batched pass over the shared generators
     launch_cross_term(L, s, ZView{f->W, f->uX, f->uX + 1}, ZView{f->W2, f->uX2, f->uX2 + 1}, f->T);
     c.launches += L.launches;
-    msm_on_device(f->gens, 0, f->T, s->cons, f->comm + 1, true);
+    const fe* vecs[2] = {f->W2, f->T};
+    const size_t lens[2] = {s->vars, s->cons};
+    msm_batch_on_device(f->gens, vecs, lens, 2, f->comm);
     d2h(comm_W2_point96_host, f->comm, sizeof(jac_t), c.stream);
     d2h(comm_T_point96_host, f->comm + 1, sizeof(jac_t), c.stream);
     VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));

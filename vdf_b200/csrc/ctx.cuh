@@ -107,4 +107,5 @@ struct vdfgpu_gens {
 // internal cross-TU entry: MSM over device scalars into a device point, on the context stream
 namespace vdf {
 void msm_on_device(vdfgpu_gens* g, size_t first, const fe* d_scalars, size_t n, jac_t* d_out, bool is_mont);
+void msm_batch_on_device(vdfgpu_gens* g, const fe* const* d_scalars, const size_t* lens, uint32_t k, jac_t* d_out);
 }

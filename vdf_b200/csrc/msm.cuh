@@ -43,6 +43,14 @@ struct MsmPlan {
   uint32_t G = 16;         // records per fixup-level thread
   uint32_t logm = 3;       // bucket-reduction chunk = 2^logm buckets
   uint32_t is_mont = 1;    // scalars arrive in Montgomery form
+  uint32_t batch = 1;      // independent scalar vectors over the SAME points (one result each), <= MSM_MAX_BATCH
+  uint32_t len[4] = {0, 0, 0, 0};  // length of each vector (<= n); shorter vectors are zero-padded
+};
+
+constexpr uint32_t MSM_MAX_BATCH = 4;
+
+struct ScalarSet {
+  const fe* v[MSM_MAX_BATCH];
 };
 
 enum MsmStage {
@@ -71,12 +79,18 @@ static inline uint32_t msm_pick_c(size_t n, bool table) {
 // ---- stage 1: digits + histogram -----------------------------------------------------------------
 template <class SF>  // SF = scalar field
 struct DigitsFn {
-  const fe* scalars;
-  uint32_t* keys;    // [W][n]: bucket_global | sign << 31, or KEY_SKIP
-  uint32_t* count;   // [NB * B]
+  ScalarSet scalars;
+  uint32_t* keys;    // [batch][W][n]: bucket_global | sign << 31, or KEY_SKIP
+  uint32_t* count;   // [batch * NB * B]
   MsmPlan p;
-  VDF_HD void operator()(size_t i) const {
-    fe s = fe_load(scalars + i);
+  VDF_HD void operator()(size_t idx) const {
+    const uint32_t bt = (uint32_t)(idx / p.n), i = (uint32_t)(idx - (size_t)bt * p.n);
+    uint32_t* kb = keys + (size_t)bt * p.W * p.n;
+    if (i >= p.len[bt]) {   // zero padding of a shorter vector
+      for (uint32_t w = 0; w < p.W; w++) kb[(size_t)w * p.n + i] = KEY_SKIP;
+      return;
+    }
+    fe s = fe_load(scalars.v[bt] + i);
     if (p.is_mont) s = SF::from_mont(s);
     uint32_t carry = 0;
     const uint32_t c = p.c, full = 1u << c;
@@ -95,12 +109,12 @@ struct DigitsFn {
         key = raw ? (raw - 1) : KEY_SKIP;
       }
       if (key != KEY_SKIP) {
-        uint32_t set = p.table ? 0u : w;
+        uint32_t set = bt * p.NB + (p.table ? 0u : w);
         uint32_t gb = set * p.B + (key & 0x7fffffffu);
         atomic_add_u32(count + gb, 1u);
         key = gb | (key & 0x80000000u);
       }
-      keys[(size_t)w * p.n + i] = key;
+      kb[(size_t)w * p.n + i] = key;
     }
   }
 };
@@ -116,7 +130,8 @@ struct ScatterFn {
     uint32_t key = keys[e];
     if (key == KEY_SKIP) return;
     uint32_t gb = key & 0x7fffffffu;
-    uint32_t w = (uint32_t)(e / p.n), i = (uint32_t)(e - (size_t)w * p.n);
+    uint32_t row = (uint32_t)(e / p.n), i = (uint32_t)(e - (size_t)row * p.n);   // row = batch * W + w
+    uint32_t w = row % p.W;
     uint32_t ref = p.table ? (uint32_t)(w * p.level_stride + i) : i;
     uint32_t pos = offs[gb] + atomic_add_u32(fill + gb, 1u);
     sref[pos] = ref | (key & 0x80000000u);
@@ -298,6 +313,46 @@ struct ReduceLevelFn {
   }
 };
 
+// Small bucket sets (latency path): sum_j j*B_j = 2^(c-1)*B_top + sum_b 2^b * S_b with S_b the sum of the
+// buckets j < B whose index has bit b set.  All S_b are plain tree sums (log depth, no serial running sums).
+// First level: thread (set, b, q) adds the two buckets number 2q and 2q+1 among those with bit b set.
+template <class C>
+struct BitPairFn {
+  const xyzz_t* buckets;  // [sets][B], element k holds digit value k+1
+  uint32_t B, nbits;      // nbits = log2(B): weights < B use bits 0..nbits-1
+  xyzz_t* out;            // [sets * nbits][B/4]
+  VDF_HD static uint32_t insert_bit(uint32_t t, uint32_t b) {   // value with bit b set, other bits from t
+    return ((t >> b) << (b + 1)) | (1u << b) | (t & ((1u << b) - 1u));
+  }
+  VDF_HD void operator()(size_t idx) const {
+    const uint32_t q4 = B / 4;
+    uint32_t row = (uint32_t)(idx / q4), q = (uint32_t)(idx - (size_t)row * q4);
+    uint32_t set = row / nbits, b = row - set * nbits;
+    const xyzz_t* bk = buckets + (size_t)set * B;
+    xyzz_t acc = bk[insert_bit(2 * q, b) - 1];
+    C::add(acc, bk[insert_bit(2 * q + 1, b) - 1]);
+    out[(size_t)row * q4 + q] = acc;
+  }
+};
+
+// one thread per bucket set: R_set = 2^(c-1) * B_top + sum_b 2^b * S_b by Horner over the bit sums
+template <class C>
+struct BitHornerFn {
+  const xyzz_t* bitsum;   // [sets * nbits][stride], element 0 of each row is S_b
+  size_t stride;
+  const xyzz_t* buckets;  // [sets][B]
+  uint32_t B, nbits;
+  xyzz_t* out;            // [sets]
+  VDF_HD void operator()(size_t set) const {
+    xyzz_t acc = buckets[set * B + (B - 1)];   // digit value B = 2^(c-1)
+    for (uint32_t b = nbits; b > 0; b--) {
+      acc = C::dbl(acc);
+      C::add(acc, bitsum[(set * nbits + (b - 1)) * stride]);
+    }
+    out[set] = acc;
+  }
+};
+
 // segmented tree sum: out[set][t] = sum of in[set][t*K .. (t+1)*K)
 template <class C>
 struct SumFn {
@@ -319,30 +374,130 @@ struct SumFn {
 // ---- stage 7: final (one thread) -----------------------------------------------------------------------
 template <class C>
 struct FinalFn {
-  const xyzz_t* in;   // [NB][in_stride], cnt used per row
+  const xyzz_t* in;   // [batch * NB][in_stride], cnt used per row
   size_t in_stride;
   uint32_t cnt, NB, c;
-  jac_t* out;
-  VDF_HD void operator()(size_t) const {
+  jac_t* out;         // [batch]
+  VDF_HD void operator()(size_t bt) const {
     xyzz_t total = C::identity();
     for (uint32_t s = NB; s > 0; s--) {
       if (s != NB)
         for (uint32_t k = 0; k < c; k++) total = C::dbl(total);
-      const xyzz_t* row = in + (size_t)(s - 1) * in_stride;
+      const xyzz_t* row = in + ((size_t)bt * NB + (s - 1)) * in_stride;
       for (uint32_t j = 0; j < cnt; j++) C::add(total, row[j]);
     }
-    *out = C::to_jac_normalised(total);
+    out[bt] = C::to_jac_normalised(total);
   }
 };
+
+// per_set[s] = sum_{k=0}^{B-1} (k+1) * arr[s][k] for B a power of two, by bit decomposition (log depth):
+//   = 2^(log2 B) * arr[B-1] + sum_b 2^b * S_b,  S_b = sum of the elements whose weight < B has bit b set.
+template <class L, class C>
+void msm_bit_weighted_sum(L& L_, uint32_t NBT, const xyzz_t* arr, uint32_t B, xyzz_t* per_set) {
+  uint32_t nbits = 0;
+  while ((1u << nbits) < B) nbits++;          // weights 1..B-1 use bits 0..nbits-1; weight B = 2^nbits
+  const uint32_t rows = NBT * nbits;
+  uint32_t cnt = B / 4;
+  xyzz_t* bs_a = L_.template alloc<xyzz_t>((size_t)rows * cnt);
+  xyzz_t* bs_b = L_.template alloc<xyzz_t>((size_t)rows * ((cnt + 3) / 4));
+  L_.template run<128>((size_t)rows * cnt, BitPairFn<C>{arr, B, nbits, bs_a});
+  const xyzz_t* cur = bs_a;
+  size_t cur_stride = cnt;
+  xyzz_t* dst = bs_b;
+  while (cnt > 1) {
+    uint32_t T = (cnt + 3) / 4;
+    L_.template run<128>((size_t)rows * T, SumFn<C>{cur, cur_stride, cnt, T, 4u, dst, T});
+    cur = dst;
+    cur_stride = T;
+    cnt = T;
+    dst = (dst == bs_a) ? bs_b : bs_a;
+  }
+  L_.template run<32>(NBT, BitHornerFn<C>{cur, cur_stride, arr, B, nbits, per_set});
+  L_.free(bs_a); L_.free(bs_b);
+}
+
+// per_set[s] = sumA[s] + 2^logm * wsum[s]
+template <class C>
+struct CombineFn {
+  const xyzz_t* sumA;   // [sets][stride], element 0
+  size_t stride;
+  const xyzz_t* wsum;   // [sets]
+  uint32_t logm;
+  xyzz_t* out;
+  VDF_HD void operator()(size_t set) const {
+    xyzz_t acc = wsum[set];
+    for (uint32_t k = 0; k < logm; k++) acc = C::dbl(acc);
+    C::add(acc, sumA[set * stride]);
+    out[set] = acc;
+  }
+};
+
+// fallback of stage 6/7 for odd sizes: chunked running sums, recursively, then a tree sum and the final thread
+template <class L, class C>
+void msm_reduce_tree(L& L_, const MsmPlan& p, uint32_t NBT, const xyzz_t* buckets, jac_t* out) {
+  const uint32_t m = 1u << p.logm;
+  // level sizes
+  uint32_t cnts[32], Ts[32];
+  int levels = 0;
+  size_t acat_len = 0;
+  for (uint32_t cnt = p.B;;) {
+    uint32_t T = (cnt + m - 1) / m;
+    cnts[levels] = cnt; Ts[levels] = T;
+    levels++;
+    acat_len += T;
+    if (T <= 1) break;
+    cnt = T - 1;
+  }
+  xyzz_t* acat = L_.template alloc<xyzz_t>((size_t)NBT * acat_len);
+  xyzz_t* lvl_a = L_.template alloc<xyzz_t>((size_t)NBT * Ts[0]);
+  xyzz_t* lvl_b = L_.template alloc<xyzz_t>((size_t)NBT * (levels > 1 ? Ts[1] : 1));
+  {
+    const xyzz_t* in = buckets;
+    size_t in_stride = p.B;
+    size_t off = 0;
+    xyzz_t* nxt = lvl_a;
+    for (int l = 0; l < levels; l++) {
+      L_.template run<128>((size_t)NBT * Ts[l],
+                           ReduceLevelFn<C>{in, in_stride, cnts[l], Ts[l], p.logm, nxt, acat, acat_len, off,
+                                            p.logm * (uint32_t)l});
+      off += Ts[l];
+      in = nxt;
+      in_stride = Ts[l];
+      nxt = (nxt == lvl_a) ? lvl_b : lvl_a;
+    }
+  }
+  // tree sum of acat rows
+  const uint32_t K = 16;
+  xyzz_t* sum_a = L_.template alloc<xyzz_t>((size_t)NBT * ((acat_len + K - 1) / K));
+  xyzz_t* sum_b = L_.template alloc<xyzz_t>((size_t)NBT * ((acat_len + (size_t)K * K - 1) / ((size_t)K * K)));
+  const xyzz_t* cur = acat;
+  size_t cur_stride = acat_len;
+  uint32_t cur_cnt = (uint32_t)acat_len;
+  xyzz_t* dst = sum_a;
+  while (cur_cnt > 1) {
+    uint32_t T = (cur_cnt + K - 1) / K;
+    L_.template run<128>((size_t)NBT * T, SumFn<C>{cur, cur_stride, cur_cnt, T, K, dst, T});
+    cur = dst;
+    cur_stride = T;
+    cur_cnt = T;
+    dst = (dst == sum_a) ? sum_b : sum_a;
+  }
+  L_.mark(MSM_STAGE_FINAL);
+  L_.template run<32>(p.batch, FinalFn<C>{cur, cur_stride, cur_cnt, p.NB, p.c, out});
+  L_.mark(MSM_STAGE_END);
+
+  L_.free(acat); L_.free(lvl_a); L_.free(lvl_b); L_.free(sum_a); L_.free(sum_b);
+}
 
 // ---- driver ------------------------------------------------------------------------------------------
 // C = curve (coordinate field), SF = its scalar field.  All pointers are in the policy's memory space.
 template <class L, class C, class SF>
-void msm_run(L& L_, const MsmPlan& p, const affine_t* pts, const fe* scalars, jac_t* out) {
-  const size_t n = p.n, E = n * p.W;
-  const uint32_t NBK = p.NB * p.B;
+void msm_run(L& L_, const MsmPlan& p, const affine_t* pts, const ScalarSet& scalars, jac_t* out) {
+  const size_t n = p.n, E = n * p.W * p.batch;
+  const uint32_t NBT = p.NB * p.batch;       // bucket sets in flight
+  const uint32_t NBK = NBT * p.B;
   if (n == 0) {
-    L_.zero(out, sizeof(jac_t));
+    L_.zero(out, sizeof(jac_t) * p.batch);
     return;
   }
   uint32_t* keys = L_.template alloc<uint32_t>(E);
@@ -356,7 +511,7 @@ void msm_run(L& L_, const MsmPlan& p, const affine_t* pts, const fe* scalars, ja
   L_.zero(buckets, (size_t)NBK * sizeof(xyzz_t));
 
   L_.mark(MSM_STAGE_DIGITS);
-  L_.template run<256>(n, DigitsFn<SF>{scalars, keys, count, p});
+  L_.template run<256>(n * p.batch, DigitsFn<SF>{scalars, keys, count, p});
   L_.mark(MSM_STAGE_SCAN);
   L_.exclusive_scan(count, offs, NBK);
   L_.mark(MSM_STAGE_SCATTER);
@@ -374,8 +529,14 @@ void msm_run(L& L_, const MsmPlan& p, const affine_t* pts, const fe* scalars, ja
   RecHdr* hdr_b = nullptr;
   xyzz_t* pt_b = nullptr;
   L_.mark(MSM_STAGE_RECORDS);
-  const uint32_t G = p.G < 4 ? 4u : p.G;  // each level maps G records to <= 2: needs G > 2 to shrink
-  while (n_rec > 4096) {
+  // Each level maps G records to <= 2 (needs G > 2 to shrink).  Large problems: G = p.G (work-efficient),
+  // stop at 4096 records.  Small problems are latency-bound (every level is a serial chain of <= G point
+  // additions, and the owner pass is serial in the number of pieces of the heaviest bucket): G = 8, run
+  // the levels down to 256 records.
+  const bool small = n_rec <= (1u << 17);
+  const uint32_t G = small ? 8u : (p.G < 4 ? 4u : p.G);
+  const size_t rec_stop = small ? 256 : 4096;
+  while (n_rec > rec_stop) {
     size_t groups = (n_rec + G - 1) / G;
     if (!hdr_b) {
       hdr_b = L_.template alloc<RecHdr>(2 * groups);
@@ -388,62 +549,53 @@ void msm_run(L& L_, const MsmPlan& p, const affine_t* pts, const fe* scalars, ja
   }
   L_.template run<128>(n_rec, RecOwnerFn<C>{hdr_a, pt_a, n_rec, buckets});
 
-  // bucket reduction tree
   L_.mark(MSM_STAGE_REDUCE);
-  const uint32_t m = 1u << p.logm;
-  // level sizes
-  uint32_t cnts[32], Ts[32];
-  int levels = 0;
-  size_t acat_len = 0;
-  for (uint32_t cnt = p.B;;) {
-    uint32_t T = (cnt + m - 1) / m;
-    cnts[levels] = cnt; Ts[levels] = T;
-    levels++;
-    acat_len += T;
-    if (T <= 1) break;
-    cnt = T - 1;
-  }
-  xyzz_t* acat = L_.template alloc<xyzz_t>((size_t)p.NB * acat_len);
-  xyzz_t* lvl_a = L_.template alloc<xyzz_t>((size_t)p.NB * Ts[0]);
-  xyzz_t* lvl_b = L_.template alloc<xyzz_t>((size_t)p.NB * (levels > 1 ? Ts[1] : 1));
-  {
-    const xyzz_t* in = buckets;
-    size_t in_stride = p.B;
-    size_t off = 0;
-    xyzz_t* nxt = lvl_a;
-    for (int l = 0; l < levels; l++) {
-      L_.template run<128>((size_t)p.NB * Ts[l],
-                           ReduceLevelFn<C>{in, in_stride, cnts[l], Ts[l], p.logm, nxt, acat, acat_len, off,
-                                            p.logm * (uint32_t)l});
-      off += Ts[l];
-      in = nxt;
-      in_stride = Ts[l];
-      nxt = (nxt == lvl_a) ? lvl_b : lvl_a;
+  const uint32_t m = 1u << p.logm, T0 = p.B / m;
+  if (p.B >= 8 && p.B <= 32768) {
+    // latency path: bit-decomposition sums of the buckets themselves
+    xyzz_t* per_set = L_.template alloc<xyzz_t>(NBT);
+    msm_bit_weighted_sum<L, C>(L_, NBT, buckets, p.B, per_set);
+    L_.mark(MSM_STAGE_FINAL);
+    L_.template run<32>(p.batch, FinalFn<C>{per_set, 1, 1u, p.NB, p.c, out});
+    L_.mark(MSM_STAGE_END);
+    L_.free(per_set);
+  } else if (p.B % m == 0 && (T0 & (T0 - 1)) == 0 && T0 >= 8 && T0 <= 65536) {
+    // throughput path: ONE level of chunked running sums where parallelism is plentiful (B/m threads),
+    // then the bit-decomposition on the B/m chunk totals and a tree sum of the chunk-local weighted sums:
+    //   sum_j j*B_j = sum_t A_t + m * sum_t t*S_t
+    xyzz_t* S_arr = L_.template alloc<xyzz_t>((size_t)NBT * T0);
+    xyzz_t* A_arr = L_.template alloc<xyzz_t>((size_t)NBT * T0);
+    L_.zero(S_arr, (size_t)NBT * T0 * sizeof(xyzz_t));   // element T0-1 (weight T0) stays the identity
+    L_.template run<128>((size_t)NBT * T0, ReduceLevelFn<C>{buckets, p.B, p.B, T0, p.logm, S_arr, A_arr, T0, 0, 0u});
+    xyzz_t* wsum = L_.template alloc<xyzz_t>(NBT);
+    msm_bit_weighted_sum<L, C>(L_, NBT, S_arr, T0, wsum);
+    // plain tree sum of A (radix 4)
+    xyzz_t* ta = L_.template alloc<xyzz_t>((size_t)NBT * ((T0 + 3) / 4));
+    xyzz_t* tb = L_.template alloc<xyzz_t>((size_t)NBT * ((T0 + 15) / 16));
+    const xyzz_t* cur = A_arr;
+    size_t cur_stride = T0;
+    uint32_t cnt = T0;
+    xyzz_t* dst = ta;
+    while (cnt > 1) {
+      uint32_t T = (cnt + 3) / 4;
+      L_.template run<128>((size_t)NBT * T, SumFn<C>{cur, cur_stride, cnt, T, 4u, dst, T});
+      cur = dst;
+      cur_stride = T;
+      cnt = T;
+      dst = (dst == ta) ? tb : ta;
     }
+    xyzz_t* per_set = L_.template alloc<xyzz_t>(NBT);
+    L_.template run<32>(NBT, CombineFn<C>{cur, cur_stride, wsum, p.logm, per_set});
+    L_.mark(MSM_STAGE_FINAL);
+    L_.template run<32>(p.batch, FinalFn<C>{per_set, 1, 1u, p.NB, p.c, out});
+    L_.mark(MSM_STAGE_END);
+    L_.free(S_arr); L_.free(A_arr); L_.free(wsum); L_.free(ta); L_.free(tb); L_.free(per_set);
+  } else {
+    msm_reduce_tree<L, C>(L_, p, NBT, buckets, out);
   }
-  // tree sum of acat rows
-  const uint32_t K = 16;
-  xyzz_t* sum_a = L_.template alloc<xyzz_t>((size_t)p.NB * ((acat_len + K - 1) / K));
-  xyzz_t* sum_b = L_.template alloc<xyzz_t>((size_t)p.NB * ((acat_len + (size_t)K * K - 1) / ((size_t)K * K)));
-  const xyzz_t* cur = acat;
-  size_t cur_stride = acat_len;
-  uint32_t cur_cnt = (uint32_t)acat_len;
-  xyzz_t* dst = sum_a;
-  while (cur_cnt > 1) {
-    uint32_t T = (cur_cnt + K - 1) / K;
-    L_.template run<128>((size_t)p.NB * T, SumFn<C>{cur, cur_stride, cur_cnt, T, K, dst, T});
-    cur = dst;
-    cur_stride = T;
-    cur_cnt = T;
-    dst = (dst == sum_a) ? sum_b : sum_a;
-  }
-  L_.mark(MSM_STAGE_FINAL);
-  L_.template run<32>(1, FinalFn<C>{cur, cur_stride, cur_cnt, p.NB, p.c, out});
-  L_.mark(MSM_STAGE_END);
 
   L_.free(keys); L_.free(count); L_.free(fill); L_.free(offs); L_.free(sref); L_.free(buckets);
   L_.free(hdr_a); L_.free(pt_a); L_.free(hdr_b); L_.free(pt_b);
-  L_.free(acat); L_.free(lvl_a); L_.free(lvl_b); L_.free(sum_a); L_.free(sum_b);
 }
 
 // ---- generator-set construction ----------------------------------------------------------------------
