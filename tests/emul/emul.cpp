@@ -116,6 +116,49 @@ int emul_msm_batch(int curve, int table, uint32_t c, uint32_t S, const void* aff
   return 0;
 }
 
+// the host API's chunked schedule: stages 1-5 per point-range chunk into one bucket array, stages 6-7 once
+int emul_msm_chunked(int curve, int table, uint32_t c, uint32_t S, const void* affine72, size_t n, const void* scalars,
+                     uint32_t chunks, void* out96) {
+  HostLaunch L;
+  uint32_t W = table ? msm_windows(c) : 1;
+  std::vector<affine_t> pts((size_t)W * (n ? n : 1));
+  L.run(n, RepackFn{(const uint8_t*)affine72, pts.data()});
+  if (table)
+    for (uint32_t l = 1; l < W; l++) {
+      size_t threads = (n + 7) / 8;
+      if (curve == 0) L.run(threads, TableLevelFn<Pallas, Fp>{pts.data() + (size_t)(l - 1) * n, pts.data() + (size_t)l * n, n, c});
+      else L.run(threads, TableLevelFn<Vesta, Fq>{pts.data() + (size_t)(l - 1) * n, pts.data() + (size_t)l * n, n, c});
+    }
+  MsmPlan full = plan_for(n, n, table, c, S, 8, 3, 1);
+  std::vector<fe> sc(n + 1);
+  std::memcpy(sc.data(), scalars, n * 32);
+  std::vector<xyzz_t> buckets((size_t)full.NB * full.B), chunk_buckets((size_t)full.NB * full.B);
+  std::memset(buckets.data(), 0, buckets.size() * sizeof(xyzz_t));
+  size_t per = (n + chunks - 1) / chunks;
+  for (uint32_t k = 0; k < chunks; k++) {
+    size_t lo = k * per, len = lo < n ? (lo + per <= n ? per : n - lo) : 0;
+    if (!len) continue;
+    MsmPlan p = full;
+    p.n = (uint32_t)len;
+    p.len[0] = (uint32_t)len;
+    ScalarSet ss{{sc.data() + lo, nullptr, nullptr, nullptr}};
+    xyzz_t* dst = k ? chunk_buckets.data() : buckets.data();
+    if (k) std::memset(dst, 0, chunk_buckets.size() * sizeof(xyzz_t));
+    if (curve == 0) {
+      msm_accumulate<HostLaunch, Pallas, Fq>(L, p, pts.data() + lo, ss, dst);
+      if (k) msm_merge_buckets<HostLaunch, Pallas>(L, full, buckets.data(), chunk_buckets.data());
+    } else {
+      msm_accumulate<HostLaunch, Vesta, Fp>(L, p, pts.data() + lo, ss, dst);
+      if (k) msm_merge_buckets<HostLaunch, Vesta>(L, full, buckets.data(), chunk_buckets.data());
+    }
+  }
+  jac_t out;
+  if (curve == 0) msm_finish<HostLaunch, Pallas>(L, full, buckets.data(), &out);
+  else msm_finish<HostLaunch, Vesta>(L, full, buckets.data(), &out);
+  std::memcpy(out96, &out, 96);
+  return 0;
+}
+
 int emul_progression(int curve, const void* k0, const void* d, size_t n, void* out72) {
   HostLaunch L;
   fe fk0, fd;

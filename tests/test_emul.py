@@ -180,3 +180,21 @@ def test_msm_batch(emul, table):
                                    ptr(lens), k, ptr(out)) == 0
         for j, v in enumerate(use):
             assert out.tobytes()[96 * j:96 * j + 96] == O.jac_to_bytes(cv, cv.msm_known_dlog(v, 8, 3)), (k, j)
+
+
+@pytest.mark.parametrize("table", [0, 1])
+def test_msm_chunked(emul, table):
+    """Point-range chunks accumulating into one bucket array (the host API's H2D/compute overlap schedule)."""
+    cv = O.VESTA
+    rng, py = O.XorShiftRng(), random.Random(21)
+    n = 333
+    pts = cv.progression(6, 13, n)
+    pts[100] = None
+    sc = nova_like_scalars(py, rng, cv.order, n)
+    sc[5], sc[200] = cv.order - 1, 0
+    want = O.jac_to_bytes(cv, cv.msm(sc, pts))
+    for c, S, chunks in ((5, 7, 1), (5, 7, 2), (6, 16, 4), (9, 11, 8), (3, 5, 3)):
+        out = np.zeros(96, np.uint8)
+        assert emul.emul_msm_chunked(1, table, c, S, ptr(aligned(O.affines_to_bytes(cv, pts))), SZ(n),
+                                     ptr(aligned(O.fes_to_bytes(sc, cv.order))), chunks, ptr(out)) == 0
+        assert out.tobytes() == want, (c, S, chunks)

@@ -145,3 +145,21 @@ def test_msm_batch_dev(gpu_lib):
     raw = out.cpu().numpy().tobytes()
     for j, v in enumerate(vecs):
         assert O.jac_from_bytes(cv, raw[96 * j:96 * j + 96]) == cv.msm_known_dlog(v, k0, d)
+
+
+@pytest.mark.parametrize("table", [False, True])
+def test_msm_host_chunked_overlap(gpu_lib, table, monkeypatch):
+    """vdfgpu_msm's chunked schedule (H2D of chunk k+1 under the accumulation of chunk k, one bucket array):
+    forced on a small input, ragged last chunk, identical bytes to the single-pass result."""
+    cv = O.PALLAS
+    rng, py = O.XorShiftRng(), random.Random(8)
+    n, k0, d = 5001, 3, 7
+    sc = nova_like_scalars(py, rng, cv.order, n)
+    g = G.Generators.progression(cv.cid, k0, d, n, table=table)
+    sb = O.fes_to_bytes(sc, cv.order)
+    monkeypatch.setenv("VDFGPU_MSM_CHUNKS", "1")
+    single = g.commit_bytes(sb)
+    for chunks in ("2", "4", "7"):
+        monkeypatch.setenv("VDFGPU_MSM_CHUNKS", chunks)
+        assert g.commit_bytes(sb) == single
+    assert O.jac_from_bytes(cv, single) == cv.msm_known_dlog(sc, k0, d)

@@ -26,6 +26,9 @@ struct Context {
   int device = -1;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;  // stream in use (own_stream or the caller's)
+  cudaStream_t copy_stream = nullptr;       // H2D of scalar chunks, overlapped with compute (vdfgpu_msm)
+  cudaEvent_t chunk_ev[8] = {};             // chunk k of the scalars has arrived
+  cudaEvent_t start_ev = nullptr;
   uint64_t launches = 0;
   StageProfile prof;      // stage timing of the most recent MSM (vdfgpu_profile_*)
 };

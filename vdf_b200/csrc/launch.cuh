@@ -38,11 +38,9 @@ VDF_HD uint32_t atomic_add_u32(uint32_t* p, uint32_t v) {
       throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(e__));              \
   } while (0)
 
-#ifndef VDF_MIN_BLOCKS
-#define VDF_MIN_BLOCKS 1
-#endif
-template <int BLOCK, class Fn>
-__global__ void __launch_bounds__(BLOCK, VDF_MIN_BLOCKS) functor_kernel(Fn f, size_t n) {
+// MINB = minimum resident blocks per SM the register allocation must allow (occupancy knob per kernel)
+template <int BLOCK, int MINB, class Fn>
+__global__ void __launch_bounds__(BLOCK, MINB) functor_kernel(Fn f, size_t n) {
   size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
   if (i < n) f(i);
 }
@@ -179,11 +177,11 @@ struct CudaLaunch {
   void zero(void* p, size_t bytes) { VDF_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, stream)); }
   void fill_ff(void* p, size_t bytes) { VDF_CUDA_CHECK(cudaMemsetAsync(p, 0xff, bytes, stream)); }
 
-  template <int BLOCK = 256, class Fn>
+  template <int BLOCK = 256, int MINB = 1, class Fn>
   void run(size_t n, Fn f) {
     if (n == 0) return;
     size_t blocks = (n + BLOCK - 1) / BLOCK;
-    functor_kernel<BLOCK, Fn><<<(unsigned)blocks, BLOCK, 0, stream>>>(f, n);
+    functor_kernel<BLOCK, MINB, Fn><<<(unsigned)blocks, BLOCK, 0, stream>>>(f, n);
     VDF_CUDA_CHECK(cudaGetLastError());
     launches++;
   }
@@ -216,7 +214,7 @@ struct HostLaunch {
   void free(void* p) { std::free(p); }
   void zero(void* p, size_t bytes) { std::memset(p, 0, bytes); }
   void fill_ff(void* p, size_t bytes) { std::memset(p, 0xff, bytes); }
-  template <int BLOCK = 256, class Fn>
+  template <int BLOCK = 256, int MINB = 1, class Fn>
   void run(size_t n, Fn f) {
     for (size_t i = 0; i < n; i++) f(i);
     launches++;

@@ -156,6 +156,22 @@ VDF_HD uint32_t upper_bound_u32(const uint32_t* a, uint32_t n, uint32_t x) {
   return lo;
 }
 
+// Chunked MSMs: every chunk accumulates into its OWN zeroed bucket array with plain stores (an addition inside
+// the divergent flush path would serialise the warp), and this fully converged kernel folds it into the
+// running array afterwards: total[b] += chunk[b].
+template <class C>
+struct BucketMergeFn {
+  xyzz_t* total;
+  const xyzz_t* chunk;
+  VDF_HD void operator()(size_t b) const {
+    xyzz_t c = chunk[b];
+    if (C::is_inf(c)) return;
+    xyzz_t t = total[b];
+    C::add(t, c);
+    total[b] = t;
+  }
+};
+
 template <class C>
 struct AccumulateFn {
   const uint32_t* offs;  // [NBK + 1]
@@ -190,6 +206,13 @@ struct AccumulateFn {
         seg_start = pos;
         acc = C::identity();
       }
+#if defined(__CUDA_ARCH__) && defined(VDF_ACC_PREFETCH)
+      // pull the point needed VDF_ACC_PREFETCH iterations ahead towards L1/L2 while this addition computes
+      if (pos + VDF_ACC_PREFETCH < hi) {
+        const affine_t* nxt = pts + (sref[pos + VDF_ACC_PREFETCH] & 0x7fffffffu);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt));
+      }
+#endif
       uint32_t ref = sref[pos];
       affine_t pt;
       const affine_t* src = pts + (ref & 0x7fffffffu);
@@ -491,24 +514,23 @@ void msm_reduce_tree(L& L_, const MsmPlan& p, uint32_t NBT, const xyzz_t* bucket
 
 // ---- driver ------------------------------------------------------------------------------------------
 // C = curve (coordinate field), SF = its scalar field.  All pointers are in the policy's memory space.
+// Stages 1-5 for ONE chunk of the points: p.n = chunk length, pts / scalars point at the chunk.  The
+// chunk's bucket sums are STORED into `buckets` ([batch*NB*B], zeroed by the caller).  Chunking lets the host
+// API overlap the H2D copy of the next chunk of scalars with the accumulation of the current one while paying
+// the bucket reduction only once (msm_merge_buckets folds the per-chunk arrays together).
 template <class L, class C, class SF>
-void msm_run(L& L_, const MsmPlan& p, const affine_t* pts, const ScalarSet& scalars, jac_t* out) {
+void msm_accumulate(L& L_, const MsmPlan& p, const affine_t* pts, const ScalarSet& scalars, xyzz_t* buckets) {
   const size_t n = p.n, E = n * p.W * p.batch;
   const uint32_t NBT = p.NB * p.batch;       // bucket sets in flight
   const uint32_t NBK = NBT * p.B;
-  if (n == 0) {
-    L_.zero(out, sizeof(jac_t) * p.batch);
-    return;
-  }
+  if (n == 0) return;
   uint32_t* keys = L_.template alloc<uint32_t>(E);
   uint32_t* count = L_.template alloc<uint32_t>(NBK);
   uint32_t* fill = L_.template alloc<uint32_t>(NBK);
   uint32_t* offs = L_.template alloc<uint32_t>((size_t)NBK + 1);
   uint32_t* sref = L_.template alloc<uint32_t>(E);
-  xyzz_t* buckets = L_.template alloc<xyzz_t>(NBK);
   L_.zero(count, (size_t)NBK * 4);
   L_.zero(fill, (size_t)NBK * 4);
-  L_.zero(buckets, (size_t)NBK * sizeof(xyzz_t));
 
   L_.mark(MSM_STAGE_DIGITS);
   L_.template run<256>(n * p.batch, DigitsFn<SF>{scalars, keys, count, p});
@@ -523,7 +545,7 @@ void msm_run(L& L_, const MsmPlan& p, const affine_t* pts, const ScalarSet& scal
   RecHdr* hdr_a = L_.template alloc<RecHdr>(n_rec);
   xyzz_t* pt_a = L_.template alloc<xyzz_t>(n_rec);
   L_.mark(MSM_STAGE_ACCUMULATE);
-  L_.template run<128>(T_acc, AccumulateFn<C>{offs, NBK, sref, pts, buckets, hdr_a, pt_a, p.S});
+  L_.template run<128, 5>(T_acc, AccumulateFn<C>{offs, NBK, sref, pts, buckets, hdr_a, pt_a, p.S});
 
   // segmented reduction of the records: log-depth levels, then owners
   RecHdr* hdr_b = nullptr;
@@ -549,6 +571,19 @@ void msm_run(L& L_, const MsmPlan& p, const affine_t* pts, const ScalarSet& scal
   }
   L_.template run<128>(n_rec, RecOwnerFn<C>{hdr_a, pt_a, n_rec, buckets});
 
+  L_.free(keys); L_.free(count); L_.free(fill); L_.free(offs); L_.free(sref);
+  L_.free(hdr_a); L_.free(pt_a); L_.free(hdr_b); L_.free(pt_b);
+}
+
+template <class L, class C>
+void msm_merge_buckets(L& L_, const MsmPlan& p, xyzz_t* total, const xyzz_t* chunk) {
+  L_.template run<128>((size_t)p.NB * p.batch * p.B, BucketMergeFn<C>{total, chunk});
+}
+
+// Stages 6-7: bucket sets -> p.batch normalised points
+template <class L, class C>
+void msm_finish(L& L_, const MsmPlan& p, const xyzz_t* buckets, jac_t* out) {
+  const uint32_t NBT = p.NB * p.batch;
   L_.mark(MSM_STAGE_REDUCE);
   const uint32_t m = 1u << p.logm, T0 = p.B / m;
   if (p.B >= 8 && p.B <= 32768) {
@@ -593,9 +628,21 @@ void msm_run(L& L_, const MsmPlan& p, const affine_t* pts, const ScalarSet& scal
   } else {
     msm_reduce_tree<L, C>(L_, p, NBT, buckets, out);
   }
+}
 
-  L_.free(keys); L_.free(count); L_.free(fill); L_.free(offs); L_.free(sref); L_.free(buckets);
-  L_.free(hdr_a); L_.free(pt_a); L_.free(hdr_b); L_.free(pt_b);
+// whole MSM in one chunk
+template <class L, class C, class SF>
+void msm_run(L& L_, const MsmPlan& p, const affine_t* pts, const ScalarSet& scalars, jac_t* out) {
+  if (p.n == 0) {
+    L_.zero(out, sizeof(jac_t) * p.batch);
+    return;
+  }
+  const size_t NBK = (size_t)p.NB * p.batch * p.B;
+  xyzz_t* buckets = L_.template alloc<xyzz_t>(NBK);
+  L_.zero(buckets, NBK * sizeof(xyzz_t));
+  msm_accumulate<L, C, SF>(L_, p, pts, scalars, buckets);
+  msm_finish<L, C>(L_, p, buckets, out);
+  L_.free(buckets);
 }
 
 // ---- generator-set construction ----------------------------------------------------------------------
