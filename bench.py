@@ -41,7 +41,7 @@ FIELD_MUL_PER_MADD = 10          # XYZZ mixed addition 8M + 2S
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=22, help="points per GPU = 2^log2n")
@@ -65,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -158,6 +158,69 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------
+def r1cs_hbm_measurements(lib, _lib, torch, log2rows: int = 21):
+    """HBM-roofline leg for the R1CS kernels: cross-term, multiply_vec and fold on an ENLARGED
+    synthetic shape (2^21 constraints, 4 non-zeros per constraint row triple: the step circuit's density) so
+    the data (about 0.5 GB) do not sit in L2.  Device-resident operands, CUDA events."""
+    import numpy as np
+    from vdf_b200.encoding import Q, fe_to_bytes
+    cons = vars_ = 1 << log2rows
+    io = 2
+    r = np.arange(cons, dtype=np.uint64)
+    one, neg1, rnd = fe_to_bytes(1, Q), fe_to_bytes(Q - 1, Q), fe_to_bytes(0x1234567890ABCDEF1234567890ABCDEF, Q)
+    a_rows, a_cols = r, r
+    b_rows, b_cols = r, (r * 7 + 3) % vars_
+    c_rows = np.concatenate([r, r])
+    c_cols = np.concatenate([(r + 1) % vars_, (r * 5) % vars_])
+    a_vals = np.frombuffer(one * cons, dtype=np.uint8)
+    b_vals = np.frombuffer(rnd * cons, dtype=np.uint8)
+    c_vals = np.frombuffer(one * cons + neg1 * cons, dtype=np.uint8)
+    h = ctypes.c_void_p()
+    _lib.check(lib.vdfgpu_r1cs_create(1, cons, vars_, io,
+                                      a_rows.ctypes.data, a_cols.ctypes.data, a_vals.ctypes.data, cons,
+                                      b_rows.ctypes.data, np.ascontiguousarray(b_cols).ctypes.data, b_vals.ctypes.data, cons,
+                                      c_rows.ctypes.data, np.ascontiguousarray(c_cols).ctypes.data, c_vals.ctypes.data, 2 * cons,
+                                      ctypes.byref(h)))
+    nnz = 4 * cons
+
+    def rand_fe(n):
+        t = torch.randint(-(1 << 63), (1 << 63) - 1, (n, 4), dtype=torch.int64, device="cuda")
+        t[:, 3] &= (1 << 62) - 1
+        return t
+
+    W1, W2, E1 = rand_fe(vars_), rand_fe(vars_), rand_fe(cons)
+    uX1, uX2, rr = rand_fe(1 + io), rand_fe(1 + io), rand_fe(1)
+    T = torch.zeros((cons, 4), dtype=torch.int64, device="cuda")
+    ABC = torch.zeros((3 * cons, 4), dtype=torch.int64, device="cuda")
+
+    def timed(fn, reps=5):
+        fn(); fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e-3
+
+    peak, src = 6650.0, "fallback"
+    mp = ROOT / "MEASURED_PEAKS.json"
+    if mp.exists():
+        peak, src = float(json.loads(mp.read_text())["hbm_gbs"]), "measured"
+    res = {"shape": {"cons": cons, "vars": vars_, "nnz": nnz}, "hbm_peak_gbs": peak, "hbm_peak_source": src}
+    t_ct = timed(lambda: _lib.check(lib.vdfgpu_cross_term_dev(h, W1.data_ptr(), uX1.data_ptr(), W2.data_ptr(), uX2.data_ptr(), T.data_ptr())))
+    b_ct = 36 * nnz + 4 * (3 * cons + 1) + 2 * 32 * (vars_ + 1 + io) + 32 * cons
+    t_mv = timed(lambda: _lib.check(lib.vdfgpu_multiply_vec_dev(h, W1.data_ptr(), uX1.data_ptr(), ABC.data_ptr())))
+    b_mv = 36 * nnz + 4 * (3 * cons + 1) + 32 * (vars_ + 1 + io) + 3 * 32 * cons
+    t_fd = timed(lambda: _lib.check(lib.vdfgpu_fold_dev(1, W1.data_ptr(), W2.data_ptr(), vars_, E1.data_ptr(), T.data_ptr(), cons, rr.data_ptr())))
+    b_fd = 96 * (vars_ + cons)
+    for name, t, b in (("cross_term", t_ct, b_ct), ("multiply_vec", t_mv, b_mv), ("fold", t_fd, b_fd)):
+        res[name] = {"ms": t * 1e3, "algorithmic_bytes": b, "achieved_gbs": b / t / 1e9, "frac_of_hbm": b / t / 1e9 / peak}
+    _lib.check(lib.vdfgpu_r1cs_destroy(h))
+    return res
+
+
 def extra_measurements(lib, _lib, torch):
     """fold-steps/s (t = 1024, synthetic augmented block) and batched verify (C4)."""
     out = {}
@@ -190,6 +253,10 @@ def extra_measurements(lib, _lib, torch):
         prover.close(); gens.close(); gs.close()
     except Exception as e:  # side measurement: never lose the headline line
         out["nifs_fold"] = {"error": repr(e)}
+    try:
+        out["r1cs_hbm"] = r1cs_hbm_measurements(lib, _lib, torch)
+    except Exception as e:
+        out["r1cs_hbm"] = {"error": repr(e)}
     try:
         n, t = 1 << 16, 1000
         res = torch.randint(0, 1 << 62, (n, 12), dtype=torch.int64, device="cuda")

@@ -116,6 +116,14 @@ int vdfgpu_commit_T(const vdfgpu_r1cs* s, vdfgpu_gens* gens, const void* W1_host
 int vdfgpu_fold(int field, void* W1_host, const void* W2_host, size_t nW, void* E1_host,
                 const void* T_host, size_t nE, const void* r32_host);
 
+/* device-pointer variants (no copies, no synchronisation): what a device-resident prover and bench.py's
+ * HBM-roofline leg call.  uX = [u | X] (1 + io elements), uX2 = [1 | X2]. */
+int vdfgpu_multiply_vec_dev(const vdfgpu_r1cs* s, const void* W_dev, const void* uX_dev, void* AzBzCz_dev);
+int vdfgpu_cross_term_dev(const vdfgpu_r1cs* s, const void* W1_dev, const void* uX1_dev, const void* W2_dev,
+                          const void* uX2_dev, void* T_dev);
+int vdfgpu_fold_dev(int field, void* W1_dev, const void* W2_dev, size_t nW, void* E1_dev, const void* T_dev,
+                    size_t nE, const void* r32_dev);
+
 /* Device-resident running instance for a chain of fold steps: W and E never leave HBM between steps.
  * One step = what NIFS::prove does with the witness: commit_T against a fresh (W2, X2), then fold with
  * the verifier challenge r (computed by the host random oracle from comm_T, so it arrives later). */

@@ -211,6 +211,49 @@ int vdfgpu_fold(int field, void* W1_host, const void* W2_host, size_t nW, void* 
   });
 }
 
+int vdfgpu_multiply_vec_dev(const vdfgpu_r1cs* s, const void* W_dev, const void* uX_dev, void* AzBzCz_dev) {
+  return guarded([&] {
+    if (!s || !uX_dev || !AzBzCz_dev || (s->vars && !W_dev)) throw ArgError("multiply_vec_dev: null pointer");
+    require_ready();
+    Context& c = ctx();
+    CudaLaunch L(c.stream);
+    const fe* ux = reinterpret_cast<const fe*>(uX_dev);
+    fe* out = reinterpret_cast<fe*>(AzBzCz_dev);
+    launch_multiply_vec(L, s, ZView{reinterpret_cast<const fe*>(W_dev), ux, ux + 1}, out, out + s->cons,
+                        out + 2 * (size_t)s->cons);
+    c.launches += L.launches;
+  });
+}
+
+int vdfgpu_cross_term_dev(const vdfgpu_r1cs* s, const void* W1_dev, const void* uX1_dev, const void* W2_dev,
+                          const void* uX2_dev, void* T_dev) {
+  return guarded([&] {
+    if (!s || !uX1_dev || !uX2_dev || !T_dev || (s->vars && (!W1_dev || !W2_dev))) throw ArgError("cross_term_dev: null pointer");
+    require_ready();
+    Context& c = ctx();
+    CudaLaunch L(c.stream);
+    const fe* u1 = reinterpret_cast<const fe*>(uX1_dev);
+    const fe* u2 = reinterpret_cast<const fe*>(uX2_dev);
+    launch_cross_term(L, s, ZView{reinterpret_cast<const fe*>(W1_dev), u1, u1 + 1},
+                      ZView{reinterpret_cast<const fe*>(W2_dev), u2, u2 + 1}, reinterpret_cast<fe*>(T_dev));
+    c.launches += L.launches;
+  });
+}
+
+int vdfgpu_fold_dev(int field, void* W1_dev, const void* W2_dev, size_t nW, void* E1_dev, const void* T_dev,
+                    size_t nE, const void* r32_dev) {
+  return guarded([&] {
+    if (field != VDFGPU_FP && field != VDFGPU_FQ) throw ArgError("fold_dev: unknown field");
+    if (!r32_dev || (nW && (!W1_dev || !W2_dev)) || (nE && (!E1_dev || !T_dev))) throw ArgError("fold_dev: null pointer");
+    require_ready();
+    Context& c = ctx();
+    CudaLaunch L(c.stream);
+    launch_fold(L, field, reinterpret_cast<fe*>(W1_dev), reinterpret_cast<const fe*>(W2_dev), nW,
+                reinterpret_cast<fe*>(E1_dev), reinterpret_cast<const fe*>(T_dev), nE, reinterpret_cast<const fe*>(r32_dev));
+    c.launches += L.launches;
+  });
+}
+
 // ---- device-resident running instance -------------------------------------------------------------------
 int vdfgpu_running_create(const vdfgpu_r1cs* s, vdfgpu_gens* gens, vdfgpu_running** out) {
   return guarded([&] {

@@ -33,14 +33,25 @@ VDF_HD fe z_at(const ZView& z, uint32_t vars, uint32_t col) {
   return fe_load(p);
 }
 
+// acc += v * x.  Most R1CS coefficients are +1 or -1 (every A/B entry and all but one C entry of the MinRoot
+// step circuit, src/nova/proof.rs:176-227): those cost an addition instead of a 245-instruction multiplication,
+// which is what moves these kernels from the multiply pipe back to the HBM roofline.  Exact either way.
+template <class F>
+VDF_HD fe mul_acc(const fe& acc, const fe& v, const fe& x, const fe& one, const fe& minus_one) {
+  if (F::eq(v, one)) return F::add(acc, x);
+  if (F::eq(v, minus_one)) return F::sub(acc, x);
+  return F::add(acc, F::mul(v, x));
+}
+
 template <class F>
 VDF_HD fe csr_row_dot(const CsrView& m, uint32_t row, const ZView& z) {
   fe acc = F::zero();
+  const fe one = F::one(), minus_one = F::neg(F::one());
   uint32_t lo = m.row_ptr[row], hi = m.row_ptr[row + 1];
   for (uint32_t k = lo; k < hi; k++) {
     fe v = fe_load(m.val + k);
     fe x = z_at<F>(z, m.vars, m.col[k]);
-    acc = F::add(acc, F::mul(v, x));
+    acc = mul_acc<F>(acc, v, x, one, minus_one);
   }
   return acc;
 }
@@ -70,6 +81,7 @@ struct CrossTermFn {
   VDF_HD void operator()(size_t idx) const {
     uint32_t row = (uint32_t)idx;
     fe d1[3], d2[3];
+    const fe one = F::one(), minus_one = F::neg(F::one());
     for (uint32_t mat = 0; mat < 3; mat++) {
       fe a1 = F::zero(), a2 = F::zero();
       uint32_t r = mat * m.cons + row;
@@ -77,8 +89,8 @@ struct CrossTermFn {
       for (uint32_t k = lo; k < hi; k++) {
         fe v = fe_load(m.val + k);
         uint32_t c = m.col[k];
-        a1 = F::add(a1, F::mul(v, z_at<F>(z1, m.vars, c)));
-        a2 = F::add(a2, F::mul(v, z_at<F>(z2, m.vars, c)));
+        a1 = mul_acc<F>(a1, v, z_at<F>(z1, m.vars, c), one, minus_one);
+        a2 = mul_acc<F>(a2, v, z_at<F>(z2, m.vars, c), one, minus_one);
       }
       d1[mat] = a1;
       d2[mat] = a2;
