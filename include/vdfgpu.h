@@ -151,6 +151,12 @@ int vdfgpu_minroot_check_batch_dev(int field, const void* results_dev, const voi
 int vdfgpu_minroot_inverse_eval_batch(int field, const void* results_state96_host, uint64_t t, size_t n,
                                       void* out_state96_host);
 
+/* Step-circuit witness: for each of n steps, the 4t+1 values InverseMinRootCircuit::synthesize
+ * allocates (src/nova/proof.rs:107-126, :162-189) in allocation order: per round new_x, tmp1, tmp2, new_y; then
+ * final_i.  out holds n * (4t+1) field elements. */
+int vdfgpu_minroot_witness_batch(int field, const void* results_state96_host, uint64_t t, size_t n,
+                                 void* out_fe32_host);
+
 /* per-stage device time of the most recent MSM, measured with CUDA events on the stream in use.
  * Stages: 0 digits+histogram, 1 scan, 2 scatter, 3 accumulate, 4 record fix-up, 5 bucket reduction, 6 final */
 #define VDFGPU_MSM_STAGES 7

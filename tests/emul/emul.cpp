@@ -202,6 +202,13 @@ int emul_minroot_inverse_eval(int field, const void* results, uint64_t t, size_t
   return 0;
 }
 
+int emul_minroot_witness(int field, const void* results, uint64_t t, size_t n, void* out) {
+  HostLaunch L;
+  if (field == 0) L.run(n, MinRootWitnessFn<Fp>{(const state_t*)results, t, (fe*)out});
+  else L.run(n, MinRootWitnessFn<Fq>{(const state_t*)results, t, (fe*)out});
+  return 0;
+}
+
 // R1CS: mode 0 = multiply_vec (out = Az|Bz|Cz, 3*cons elements, z1 only), mode 1 = cross-term T (cons elements)
 int emul_r1cs(int field, int mode, size_t num_cons, size_t num_vars, size_t num_io, const uint64_t* a_rows,
               const uint64_t* a_cols, const void* a_vals, size_t a_nnz, const uint64_t* b_rows, const uint64_t* b_cols,

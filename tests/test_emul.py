@@ -198,3 +198,19 @@ def test_msm_chunked(emul, table):
         assert emul.emul_msm_chunked(1, table, c, S, ptr(aligned(O.affines_to_bytes(cv, pts))), SZ(n),
                                      ptr(aligned(O.fes_to_bytes(sc, cv.order))), chunks, ptr(out)) == 0
         assert out.tobytes() == want, (c, S, chunks)
+
+
+@pytest.mark.parametrize("fid", [O.FIELD_FQ, O.FIELD_FP])
+def test_minroot_step_witness(emul, fid):
+    """Device witness generator vs the oracle's restatement of InverseMinRootCircuit::synthesize."""
+    vdf = O.MinRootVDF(fid)
+    rng = O.XorShiftRng()
+    t, n = 9, 5
+    res = [vdf.eval(O.State(O.field_random(rng, vdf.m), 0, 1), t) for _ in range(n)]
+    out = np.zeros(n * (4 * t + 1) * 32, np.uint8)
+    emul.emul_minroot_witness(fid, ptr(aligned(b"".join(O.state_to_bytes(s, vdf.m) for s in res))),
+                              ctypes.c_uint64(t), SZ(n), ptr(out))
+    got = O.fes_from_bytes(out.tobytes(), vdf.m)
+    for k, s in enumerate(res):
+        _, W, _, _ = O.make_step_instance(fid, t, s)
+        assert got[k * (4 * t + 1):(k + 1) * (4 * t + 1)] == W[3:]   # W = [x, y, i | step variables]

@@ -88,3 +88,19 @@ def test_check_batch_full_size_property(gpu_lib):
     originals = [M.State(o.x, o.y, (o.i + 1) % vdf.m) if k in bad else o for k, o in enumerate(originals)]
     ok = vdf.check_batch(results, t, originals)
     assert all(ok[k] == (k not in bad) for k in range(n))
+
+
+@pytest.mark.parametrize("V,OV,fid", [(M.PallasVDF, O.PallasVDF, O.FIELD_FQ), (M.VestaVDF, O.VestaVDF, O.FIELD_FP)])
+def test_step_witness_batch(gpu_lib, V, OV, fid):
+    """the step part of W generated on the device equals the oracle's synthesis of
+    InverseMinRootCircuit (src/nova/proof.rs:87-230) and satisfies the step shape."""
+    vdf, ovdf = V(), OV()
+    rng = O.XorShiftRng()
+    t, n = 25, 7
+    states = [ovdf.eval(O.State(O.field_random(rng, vdf.m), 0, 1), t) for _ in range(n)]
+    got = vdf.step_witness_batch([M.State(s.x, s.y, s.i) for s in states], t)
+    for s, w in zip(states, got):
+        shape, W, X, outs = O.make_step_instance(fid, t, s)
+        assert w == W[3:]
+        assert shape.is_sat_relaxed([s.x, s.y, s.i] + w, [0] * shape.num_cons, 1, X)
+    assert vdf.step_witness_batch([], t) == []

@@ -63,6 +63,7 @@ PROTOTYPES = {
     "vdfgpu_minroot_check_batch": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_uint64, c_size_t, c_void_p]),
     "vdfgpu_minroot_check_batch_dev": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_uint64, c_size_t, c_void_p]),
     "vdfgpu_minroot_inverse_eval_batch": (c_int, [c_int, c_void_p, c_uint64, c_size_t, c_void_p]),
+    "vdfgpu_minroot_witness_batch": (c_int, [c_int, c_void_p, c_uint64, c_size_t, c_void_p]),
     "vdfgpu_field_mul_batch": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_uint32, c_void_p]),
     "vdfgpu_imad_peak": (c_int, [POINTER(c_double), POINTER(c_double), POINTER(c_double)]),
 }

@@ -649,6 +649,26 @@ int vdfgpu_minroot_inverse_eval_batch(int field, const void* results_host, uint6
   });
 }
 
+int vdfgpu_minroot_witness_batch(int field, const void* results_host, uint64_t t, size_t n, void* out_host) {
+  return guarded([&] {
+    if (field != VDFGPU_FP && field != VDFGPU_FQ) throw ArgError("minroot_witness: unknown field");
+    if (n && (!results_host || !out_host)) throw ArgError("minroot_witness: null pointer");
+    if (n == 0) return;
+    require_ready();
+    Context& c = ctx();
+    CudaLaunch L(c.stream);
+    const size_t per = 4 * (size_t)t + 1;
+    DevBuf<state_t> res(n, c.stream);
+    DevBuf<fe> out(n * per, c.stream);
+    h2d(res.p, results_host, n * sizeof(state_t), c.stream);
+    if (field == VDFGPU_FP) L.run<128>(n, MinRootWitnessFn<Fp>{res.p, t, out.p});
+    else L.run<128>(n, MinRootWitnessFn<Fq>{res.p, t, out.p});
+    d2h(out_host, out.p, n * per * 32, c.stream);
+    c.launches += L.launches;
+    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  });
+}
+
 // ---- probes ---------------------------------------------------------------------------------------------
 int vdfgpu_field_mul_batch(int field, const void* a_host, const void* b_host, size_t n, uint32_t iters,
                            void* out_host) {

@@ -69,4 +69,35 @@ struct MinRootInverseEvalFn {
   }
 };
 
+// Step-circuit witness generation: the 4t+1 auxiliary values that
+// InverseMinRootCircuit::synthesize allocates for one fold step -- per round new_x, tmp1 = x^2, tmp2 = tmp1^2,
+// new_y = tmp2*x - new_x (src/nova/proof.rs:162-189), then final_i (:122-126) -- in allocation order, so the
+// result is the step part of W and can feed commit(W) without passing through the host.  One thread per step:
+// the circuits of a proof are independent once the VDF states are known (src/nova/proof.rs:284-296).
+template <class F>
+struct MinRootWitnessFn {
+  const state_t* results;   // z_in = (x, y, i) of each step
+  uint64_t t;
+  fe* out;                  // [n][4t + 1]
+  VDF_HD void operator()(size_t idx) const {
+    fe x = fe_load(&results[idx].x), y = fe_load(&results[idx].y), i = fe_load(&results[idx].i);
+    const fe one = F::one();
+    fe* w = out + idx * (4 * t + 1);
+#pragma unroll 1
+    for (uint64_t k = 0; k < t; k++) {
+      fe ni = F::sub(i, one);            // proof.rs:162-164
+      fe nx = F::sub(y, ni);             // proof.rs:167-173
+      fe t1 = F::sqr(x);                 // proof.rs:176
+      fe t2 = F::sqr(t1);                // proof.rs:178
+      fe ny = F::sub(F::mul(t2, x), nx); // proof.rs:181-189
+      fe_store(w + 4 * k + 0, nx);
+      fe_store(w + 4 * k + 1, t1);
+      fe_store(w + 4 * k + 2, t2);
+      fe_store(w + 4 * k + 3, ny);
+      x = nx; y = ny; i = ni;
+    }
+    fe_store(w + 4 * t, i);              // final_i, proof.rs:122-126
+  }
+};
+
 }  // namespace vdf

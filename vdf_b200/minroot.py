@@ -75,6 +75,20 @@ class MinRootVDF:
     def inverse_eval(self, x: State, t: int) -> State:  # minroot.rs:363-365
         return self.inverse_eval_batch([x], t)[0]
 
+    def step_witness_batch(self, results: Sequence[State], t: int) -> List[List[int]]:
+        """The 4t+1 step-circuit variables of each step (src/nova/proof.rs:107-126, :162-189), generated on the
+        GPU in allocation order: per round new_x, tmp1, tmp2, new_y; then final_i."""
+        n = len(results)
+        if n == 0:
+            return []
+        per = 4 * t + 1
+        inp = b"".join(s.to_bytes(self.m) for s in results)
+        out = bytearray(n * per * 32)
+        _lib.check(_lib.load().vdfgpu_minroot_witness_batch(self.field_id, _lib.as_ptr(inp), t, n, _lib.as_ptr(out)))
+        from .encoding import fes_from_bytes
+        vals = fes_from_bytes(bytes(out), self.m)
+        return [vals[k * per:(k + 1) * per] for k in range(n)]
+
     def check_batch_bytes(self, results: bytes, originals: bytes, t) -> List[bool]:
         n = len(results) // STATE_BYTES
         if len(originals) != len(results):
