@@ -94,6 +94,35 @@ def test_msm_known_dlog_large(gpu_lib, cid, table, log2n):
     g.close()
 
 
+def test_msm_known_dlog_2_22(gpu_lib):
+    """The benchmark's own size (BASELINE config 2 maximum, 2^22 points, table layout c = 20): known-discrete-log
+    identity, plus the same scalars through the plain layout and pasta-msm's one-shot symbol on a 2^16 prefix."""
+    import numpy as np
+    cv = O.PALLAS
+    n = 1 << 22
+    k0, d = 0x1234567, 0x89ABCDEF01
+    rs = np.random.RandomState(7)
+    raw = rs.randint(0, 1 << 32, size=(n, 8), dtype=np.uint64).astype(np.uint32)
+    raw[:, 7] &= 0x3FFFFFFF                                   # < 2^254: valid Montgomery-form limbs
+    sb = raw.tobytes()
+    g = G.Generators.progression(cv.cid, k0, d, n, table=True)
+    got = O.jac_from_bytes(cv, g.commit_bytes(sb))
+    # scalar value = limbs * R^-1: fold R^-1 out once instead of per element
+    rinv = pow(1 << 256, -1, cv.order)
+    acc = 0
+    for i in range(n):
+        acc += int.from_bytes(sb[32 * i:32 * i + 32], "little") * (k0 + i * d)
+    assert got == cv.mul(acc * rinv % cv.order, cv.gen)
+    m = 1 << 16
+    want_prefix = g.commit_bytes(sb[:32 * m])
+    gp = G.Generators.progression(cv.cid, k0, d, m, table=False)
+    assert gp.commit_bytes(sb[:32 * m]) == want_prefix
+    pts72 = bytearray(72 * m)
+    from vdf_b200 import _lib
+    _lib.check(gpu_lib.vdfgpu_gens_export(gp._h, 0, m, _lib.as_ptr(pts72)))
+    assert G.mult_pippenger(cv.cid, bytes(pts72), sb[:32 * m], True) == want_prefix
+
+
 def test_point_sum_and_sharded_combine(gpu_lib):
     """Multi-GPU path emulated as G point-range slices on one GPU: partials combined with
     vdfgpu_point_sum equal the single-range result."""
