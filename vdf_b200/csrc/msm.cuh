@@ -439,10 +439,10 @@ void msm_bit_weighted_sum(L& L_, uint32_t NBT, const xyzz_t* arr, uint32_t B, xy
   L_.free(bs_a); L_.free(bs_b);
 }
 
-// per_set[s] = sumA[s] + 2^logm * wsum[s]
+// per_set[s] = (four partial sums of A_t) + 2^logm * wsum[s]
 template <class C>
 struct CombineFn {
-  const xyzz_t* sumA;   // [sets][stride], element 0
+  const xyzz_t* sumA;   // [sets * 4][stride], element 0 of each row
   size_t stride;
   const xyzz_t* wsum;   // [sets]
   uint32_t logm;
@@ -450,7 +450,7 @@ struct CombineFn {
   VDF_HD void operator()(size_t set) const {
     xyzz_t acc = wsum[set];
     for (uint32_t k = 0; k < logm; k++) acc = C::dbl(acc);
-    C::add(acc, sumA[set * stride]);
+    for (uint32_t k = 0; k < 4; k++) C::add(acc, sumA[(set * 4 + k) * stride]);
     out[set] = acc;
   }
 };
@@ -596,35 +596,40 @@ void msm_finish(L& L_, const MsmPlan& p, const xyzz_t* buckets, jac_t* out) {
     L_.free(per_set);
   } else if (p.B % m == 0 && (T0 & (T0 - 1)) == 0 && T0 >= 8 && T0 <= 65536) {
     // throughput path: ONE level of chunked running sums where parallelism is plentiful (B/m threads),
-    // then the bit-decomposition on the B/m chunk totals and a tree sum of the chunk-local weighted sums:
+    // then the bit-decomposition on the B/m chunk totals and a plain sum of the chunk-local weighted sums:
     //   sum_j j*B_j = sum_t A_t + m * sum_t t*S_t
+    // Both tree sums share their launches: the row buffer holds nbits bit rows per set (pairs already added,
+    // length T0/4) followed by the A values viewed as four rows of length T0/4 per set.
+    uint32_t nbits = 0;
+    while ((1u << nbits) < T0) nbits++;
+    const uint32_t q4 = T0 / 4, bit_rows = NBT * nbits, rows = bit_rows + NBT * 4;
     xyzz_t* S_arr = L_.template alloc<xyzz_t>((size_t)NBT * T0);
-    xyzz_t* A_arr = L_.template alloc<xyzz_t>((size_t)NBT * T0);
+    xyzz_t* ra = L_.template alloc<xyzz_t>((size_t)rows * q4);
+    xyzz_t* rb = L_.template alloc<xyzz_t>((size_t)rows * ((q4 + 3) / 4));
+    xyzz_t* A_arr = ra + (size_t)bit_rows * q4;           // [NBT][T0] == [NBT*4][T0/4]
     L_.zero(S_arr, (size_t)NBT * T0 * sizeof(xyzz_t));   // element T0-1 (weight T0) stays the identity
     L_.template run<128>((size_t)NBT * T0, ReduceLevelFn<C>{buckets, p.B, p.B, T0, p.logm, S_arr, A_arr, T0, 0, 0u});
-    xyzz_t* wsum = L_.template alloc<xyzz_t>(NBT);
-    msm_bit_weighted_sum<L, C>(L_, NBT, S_arr, T0, wsum);
-    // plain tree sum of A (radix 4)
-    xyzz_t* ta = L_.template alloc<xyzz_t>((size_t)NBT * ((T0 + 3) / 4));
-    xyzz_t* tb = L_.template alloc<xyzz_t>((size_t)NBT * ((T0 + 15) / 16));
-    const xyzz_t* cur = A_arr;
-    size_t cur_stride = T0;
-    uint32_t cnt = T0;
-    xyzz_t* dst = ta;
+    L_.template run<128>((size_t)bit_rows * q4, BitPairFn<C>{S_arr, T0, nbits, ra});
+    const xyzz_t* cur = ra;
+    size_t cur_stride = q4;
+    uint32_t cnt = q4;
+    xyzz_t* dst = rb;
     while (cnt > 1) {
       uint32_t T = (cnt + 3) / 4;
-      L_.template run<128>((size_t)NBT * T, SumFn<C>{cur, cur_stride, cnt, T, 4u, dst, T});
+      L_.template run<128>((size_t)rows * T, SumFn<C>{cur, cur_stride, cnt, T, 4u, dst, T});
       cur = dst;
       cur_stride = T;
       cnt = T;
-      dst = (dst == ta) ? tb : ta;
+      dst = (dst == ra) ? rb : ra;
     }
+    xyzz_t* wsum = L_.template alloc<xyzz_t>(NBT);
     xyzz_t* per_set = L_.template alloc<xyzz_t>(NBT);
-    L_.template run<32>(NBT, CombineFn<C>{cur, cur_stride, wsum, p.logm, per_set});
+    L_.template run<32>(NBT, BitHornerFn<C>{cur, cur_stride, S_arr, T0, nbits, wsum});
+    L_.template run<32>(NBT, CombineFn<C>{cur + (size_t)bit_rows * cur_stride, cur_stride, wsum, p.logm, per_set});
     L_.mark(MSM_STAGE_FINAL);
     L_.template run<32>(p.batch, FinalFn<C>{per_set, 1, 1u, p.NB, p.c, out});
     L_.mark(MSM_STAGE_END);
-    L_.free(S_arr); L_.free(A_arr); L_.free(wsum); L_.free(ta); L_.free(tb); L_.free(per_set);
+    L_.free(S_arr); L_.free(ra); L_.free(rb); L_.free(wsum); L_.free(per_set);
   } else {
     msm_reduce_tree<L, C>(L_, p, NBT, buckets, out);
   }
