@@ -205,8 +205,10 @@ static vdfgpu_gens* gens_alloc(int curve, size_t n, uint32_t flags, uint32_t win
 template <class F>
 static void minroot_check_dispatch(CudaLaunch& L, const void* res, const void* orig, const uint64_t* t_each,
                                    uint64_t t_uniform, size_t n, uint8_t* ok) {
-  L.run<128>(n, MinRootCheckFn<F>{reinterpret_cast<const state_t*>(res), reinterpret_cast<const state_t*>(orig),
-                                  t_each, t_uniform, ok});
+  // 32-thread blocks: 2^16 chains are only ~3.5 blocks of 128 per SM, and whole blocks cannot be split across
+  // SMs (4 vs 3 resident blocks = 14 % imbalance); 2048 one-warp blocks spread evenly over the 148 SMs
+  L.run<32>(n, MinRootCheckFn<F>{reinterpret_cast<const state_t*>(res), reinterpret_cast<const state_t*>(orig),
+                                 t_each, t_uniform, ok});
 }
 
 template <class F>

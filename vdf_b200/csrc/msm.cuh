@@ -126,15 +126,32 @@ struct ScatterFn {
   uint32_t* fill;
   uint32_t* sref;
   MsmPlan p;
-  VDF_HD void operator()(size_t e) const {
-    uint32_t key = keys[e];
-    if (key == KEY_SKIP) return;
-    uint32_t gb = key & 0x7fffffffu;
-    uint32_t row = (uint32_t)(e / p.n), i = (uint32_t)(e - (size_t)row * p.n);   // row = batch * W + w
-    uint32_t w = row % p.W;
-    uint32_t ref = p.table ? (uint32_t)(w * p.level_stride + i) : i;
-    uint32_t pos = offs[gb] + atomic_add_u32(fill + gb, 1u);
-    sref[pos] = ref | (key & 0x80000000u);
+  size_t E;
+  static constexpr int PER = 4;   // entries per thread: four independent atomics in flight per thread
+  VDF_HD void operator()(size_t t) const {
+    // thread t handles entries t, t + T, t + 2T, t + 3T (T = number of threads) so each access stays coalesced
+    const size_t T = (E + PER - 1) / PER;
+    uint32_t key[PER], pos[PER];
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      size_t e = t + (size_t)k * T;
+      key[k] = e < E ? keys[e] : KEY_SKIP;
+    }
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      if (key[k] == KEY_SKIP) continue;
+      uint32_t gb = key[k] & 0x7fffffffu;
+      pos[k] = offs[gb] + atomic_add_u32(fill + gb, 1u);
+    }
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      if (key[k] == KEY_SKIP) continue;
+      size_t e = t + (size_t)k * T;
+      uint32_t row = (uint32_t)(e / p.n), i = (uint32_t)(e - (size_t)row * p.n);   // row = batch * W + w
+      uint32_t w = row % p.W;
+      uint32_t ref = p.table ? (uint32_t)(w * p.level_stride + i) : i;
+      sref[pos[k]] = ref | (key[k] & 0x80000000u);
+    }
   }
 };
 
@@ -537,7 +554,7 @@ void msm_accumulate(L& L_, const MsmPlan& p, const affine_t* pts, const ScalarSe
   L_.mark(MSM_STAGE_SCAN);
   L_.exclusive_scan(count, offs, NBK);
   L_.mark(MSM_STAGE_SCATTER);
-  L_.template run<256>(E, ScatterFn{keys, offs, fill, sref, p});
+  L_.template run<256>((E + ScatterFn::PER - 1) / ScatterFn::PER, ScatterFn{keys, offs, fill, sref, p, E});
 
   // accumulate over fixed-size ranges of the sorted list
   size_t T_acc = (E + p.S - 1) / p.S;
