@@ -47,6 +47,8 @@ extern "C" {
 
 /* generator-set flags */
 #define VDFGPU_GENS_TABLE 1u /* precompute 2^(c*w) * P_i levels (W x memory, one shared bucket set) */
+#define VDFGPU_GENS_RAW_JACOBIAN 2u /* results as un-normalised Jacobian (X, Y, Z), like pasta-msm returns them: skips
+                                     * the single-thread field inversion (~0.13 ms); the caller's to_affine() normalises */
 
 typedef struct vdfgpu_gens vdfgpu_gens;   /* device-resident commitment generators (nova CommitGens) */
 typedef struct vdfgpu_r1cs vdfgpu_r1cs;   /* device-resident R1CS shape in CSR (nova R1CSShape) */

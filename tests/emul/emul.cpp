@@ -50,6 +50,7 @@ MsmPlan plan_for(size_t n, size_t stride, int table, uint32_t c, uint32_t S, uin
   p.is_mont = is_mont ? 1u : 0u;
   p.batch = 1;
   p.len[0] = (uint32_t)n;
+  p.raw_jacobian = 0;
   return p;
 }
 

@@ -192,3 +192,20 @@ def test_msm_host_chunked_overlap(gpu_lib, table, monkeypatch):
         monkeypatch.setenv("VDFGPU_MSM_CHUNKS", chunks)
         assert g.commit_bytes(sb) == single
     assert O.jac_from_bytes(cv, single) == cv.msm_known_dlog(sc, k0, d)
+
+
+@pytest.mark.parametrize("cid", CURVES)
+def test_raw_jacobian_output(gpu_lib, cid):
+    """VDFGPU_GENS_RAW_JACOBIAN: the un-normalised (X, Y, Z) result is the same group element (what pasta-msm returns
+    is un-normalised too); identity stays (0, 0, 0)."""
+    cv = O.CURVES[cid]
+    rng = O.XorShiftRng()
+    n, k0, d = 3000, 9, 4
+    sc = rand_scalars(rng, cv.order, n)
+    for table in (False, True):
+        g_raw = G.Generators.progression(cid, k0, d, n, table=table, raw_jacobian=True)
+        g_nrm = G.Generators.progression(cid, k0, d, n, table=table)
+        raw, nrm = g_raw.commit_bytes(O.fes_to_bytes(sc, cv.order)), g_nrm.commit_bytes(O.fes_to_bytes(sc, cv.order))
+        assert raw != nrm and O.jac_from_bytes(cv, raw) == O.jac_from_bytes(cv, nrm) == cv.msm_known_dlog(sc, k0, d)
+        assert O.fe_from_bytes(nrm[64:96], cv.base) == 1
+        assert g_raw.commit_bytes(O.fes_to_bytes([0] * 10, cv.order)) == bytes(96)

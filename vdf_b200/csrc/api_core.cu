@@ -68,6 +68,7 @@ static MsmPlan make_plan(const vdfgpu_gens* g, size_t n, bool is_mont, uint32_t 
   p.NB = p.table ? 1u : p.W;
   p.level_stride = g->n;
   p.is_mont = is_mont ? 1u : 0u;
+  p.raw_jacobian = (g->flags & VDFGPU_GENS_RAW_JACOBIAN) ? 1u : 0u;
   // entries per accumulate thread: enough threads to fill 148 SMs, ranges long enough to amortise
   // the two boundary records each thread may emit
   size_t E = n * p.W * batch;

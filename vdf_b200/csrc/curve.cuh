@@ -192,6 +192,20 @@ struct Curve {
     return r;
   }
 
+  // un-normalised Jacobian image of an XYZZ point: Z = ZZ (= z^2 of the underlying Jacobian z), so
+  // X' = X*ZZ and Y' = Y*ZZZ satisfy X'/Z^2 = X/ZZ and Y'/Z^3 = Y/ZZZ.  Two multiplications, no inversion.
+  static VDF_HD jac_t to_jac_raw(const xyzz_t& p) {
+    jac_t r;
+    if (is_inf(p)) {
+      r.X = F::zero(); r.Y = F::zero(); r.Z = F::zero();
+      return r;
+    }
+    r.X = F::mul(p.X, p.ZZ);
+    r.Y = F::mul(p.Y, p.ZZZ);
+    r.Z = p.ZZ;
+    return r;
+  }
+
   static VDF_HD xyzz_t from_jac(const jac_t& p) {
     xyzz_t r;
     if (F::is_zero(p.Z)) return identity();

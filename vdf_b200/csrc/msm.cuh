@@ -45,6 +45,7 @@ struct MsmPlan {
   uint32_t is_mont = 1;    // scalars arrive in Montgomery form
   uint32_t batch = 1;      // independent scalar vectors over the SAME points (one result each), <= MSM_MAX_BATCH
   uint32_t len[4] = {0, 0, 0, 0};  // length of each vector (<= n); shorter vectors are zero-padded
+  uint32_t raw_jacobian = 0;       // 1: write (X*ZZ, Y*ZZZ, ZZ) without the final inversion (caller normalises)
 };
 
 constexpr uint32_t MSM_MAX_BATCH = 4;
@@ -375,21 +376,22 @@ struct BitPairFn {
   }
 };
 
-// one thread per bucket set: R_set = 2^(c-1) * B_top + sum_b 2^b * S_b by Horner over the bit sums
+// thread (set, b), b = 0..nbits: term_b = 2^b * S_b (b doublings), the last one 2^nbits * arr[B-1]; the terms are
+// summed by the caller with a short tree.  (A Horner loop over the bits would serialise nbits doublings AND
+// nbits additions in one thread; here the longest chain is nbits doublings.)
 template <class C>
-struct BitHornerFn {
+struct BitScaleFn {
   const xyzz_t* bitsum;   // [sets * nbits][stride], element 0 of each row is S_b
   size_t stride;
-  const xyzz_t* buckets;  // [sets][B]
+  const xyzz_t* arr;      // [sets][B]
   uint32_t B, nbits;
-  xyzz_t* out;            // [sets]
-  VDF_HD void operator()(size_t set) const {
-    xyzz_t acc = buckets[set * B + (B - 1)];   // digit value B = 2^(c-1)
-    for (uint32_t b = nbits; b > 0; b--) {
-      acc = C::dbl(acc);
-      C::add(acc, bitsum[(set * nbits + (b - 1)) * stride]);
-    }
-    out[set] = acc;
+  xyzz_t* out;            // [sets][nbits + 1]
+  VDF_HD void operator()(size_t idx) const {
+    const uint32_t per = nbits + 1;
+    uint32_t set = (uint32_t)(idx / per), b = (uint32_t)(idx - (size_t)set * per);
+    xyzz_t acc = b < nbits ? bitsum[((size_t)set * nbits + b) * stride] : arr[(size_t)set * B + (B - 1)];
+    for (uint32_t k = 0; k < b; k++) acc = C::dbl(acc);
+    out[idx] = acc;
   }
 };
 
@@ -418,6 +420,7 @@ struct FinalFn {
   size_t in_stride;
   uint32_t cnt, NB, c;
   jac_t* out;         // [batch]
+  uint32_t raw_jacobian;
   VDF_HD void operator()(size_t bt) const {
     xyzz_t total = C::identity();
     for (uint32_t s = NB; s > 0; s--) {
@@ -426,9 +429,35 @@ struct FinalFn {
       const xyzz_t* row = in + ((size_t)bt * NB + (s - 1)) * in_stride;
       for (uint32_t j = 0; j < cnt; j++) C::add(total, row[j]);
     }
-    out[bt] = C::to_jac_normalised(total);
+    out[bt] = raw_jacobian ? C::to_jac_raw(total) : C::to_jac_normalised(total);
   }
 };
+
+// out[set] = sum_b 2^b S_b + 2^nbits arr[B-1] from the finished bit rows
+template <class L, class C>
+void msm_bit_combine(L& L_, uint32_t NBT, const xyzz_t* bitsum, size_t stride, const xyzz_t* arr, uint32_t B,
+                     uint32_t nbits, xyzz_t* out) {
+  const uint32_t per = nbits + 1;
+  xyzz_t* terms = L_.template alloc<xyzz_t>((size_t)NBT * per);
+  xyzz_t* t1 = L_.template alloc<xyzz_t>((size_t)NBT * ((per + 3) / 4));
+  L_.template run<32>((size_t)NBT * per, BitScaleFn<C>{bitsum, stride, arr, B, nbits, terms});
+  const xyzz_t* cur = terms;
+  size_t cur_stride = per;
+  uint32_t cnt = per;
+  xyzz_t* dst = t1;
+  xyzz_t* spare = terms;
+  while (cnt > 4) {
+    uint32_t T = (cnt + 3) / 4;
+    L_.template run<32>((size_t)NBT * T, SumFn<C>{cur, cur_stride, cnt, T, 4u, dst, T});
+    cur = dst;
+    cur_stride = T;
+    cnt = T;
+    xyzz_t* nx = (dst == t1) ? spare : t1;
+    dst = nx;
+  }
+  L_.template run<32>(NBT, SumFn<C>{cur, cur_stride, cnt, 1u, cnt, out, 1});
+  L_.free(terms); L_.free(t1);
+}
 
 // per_set[s] = sum_{k=0}^{B-1} (k+1) * arr[s][k] for B a power of two, by bit decomposition (log depth):
 //   = 2^(log2 B) * arr[B-1] + sum_b 2^b * S_b,  S_b = sum of the elements whose weight < B has bit b set.
@@ -452,7 +481,7 @@ void msm_bit_weighted_sum(L& L_, uint32_t NBT, const xyzz_t* arr, uint32_t B, xy
     cnt = T;
     dst = (dst == bs_a) ? bs_b : bs_a;
   }
-  L_.template run<32>(NBT, BitHornerFn<C>{cur, cur_stride, arr, B, nbits, per_set});
+  msm_bit_combine<L, C>(L_, NBT, cur, cur_stride, arr, B, nbits, per_set);
   L_.free(bs_a); L_.free(bs_b);
 }
 
@@ -523,7 +552,7 @@ void msm_reduce_tree(L& L_, const MsmPlan& p, uint32_t NBT, const xyzz_t* bucket
     dst = (dst == sum_a) ? sum_b : sum_a;
   }
   L_.mark(MSM_STAGE_FINAL);
-  L_.template run<32>(p.batch, FinalFn<C>{cur, cur_stride, cur_cnt, p.NB, p.c, out});
+  L_.template run<32>(p.batch, FinalFn<C>{cur, cur_stride, cur_cnt, p.NB, p.c, out, p.raw_jacobian});
   L_.mark(MSM_STAGE_END);
 
   L_.free(acat); L_.free(lvl_a); L_.free(lvl_b); L_.free(sum_a); L_.free(sum_b);
@@ -608,7 +637,7 @@ void msm_finish(L& L_, const MsmPlan& p, const xyzz_t* buckets, jac_t* out) {
     xyzz_t* per_set = L_.template alloc<xyzz_t>(NBT);
     msm_bit_weighted_sum<L, C>(L_, NBT, buckets, p.B, per_set);
     L_.mark(MSM_STAGE_FINAL);
-    L_.template run<32>(p.batch, FinalFn<C>{per_set, 1, 1u, p.NB, p.c, out});
+    L_.template run<32>(p.batch, FinalFn<C>{per_set, 1, 1u, p.NB, p.c, out, p.raw_jacobian});
     L_.mark(MSM_STAGE_END);
     L_.free(per_set);
   } else if (p.B % m == 0 && (T0 & (T0 - 1)) == 0 && T0 >= 8 && T0 <= 65536) {
@@ -641,10 +670,10 @@ void msm_finish(L& L_, const MsmPlan& p, const xyzz_t* buckets, jac_t* out) {
     }
     xyzz_t* wsum = L_.template alloc<xyzz_t>(NBT);
     xyzz_t* per_set = L_.template alloc<xyzz_t>(NBT);
-    L_.template run<32>(NBT, BitHornerFn<C>{cur, cur_stride, S_arr, T0, nbits, wsum});
+    msm_bit_combine<L, C>(L_, NBT, cur, cur_stride, S_arr, T0, nbits, wsum);
     L_.template run<32>(NBT, CombineFn<C>{cur + (size_t)bit_rows * cur_stride, cur_stride, wsum, p.logm, per_set});
     L_.mark(MSM_STAGE_FINAL);
-    L_.template run<32>(p.batch, FinalFn<C>{per_set, 1, 1u, p.NB, p.c, out});
+    L_.template run<32>(p.batch, FinalFn<C>{per_set, 1, 1u, p.NB, p.c, out, p.raw_jacobian});
     L_.mark(MSM_STAGE_END);
     L_.free(S_arr); L_.free(ra); L_.free(rb); L_.free(wsum); L_.free(per_set);
   } else {

@@ -11,6 +11,7 @@ from .encoding import (AFFINE_BYTES, CURVE_BASE, CURVE_ORDER, POINT_BYTES, Affin
                        affines_to_bytes, fes_to_bytes, point_from_bytes)
 
 GENS_TABLE = 1
+GENS_RAW_JACOBIAN = 2   # results un-normalised (X, Y, Z) as pasta-msm returns them; decode with point_from_bytes
 
 
 class Generators:
@@ -21,13 +22,15 @@ class Generators:
         self._h = ctypes.c_void_p(handle)
 
     @classmethod
-    def from_affine_bytes(cls, curve: int, data: bytes, table: bool = False, window_bits: int = 0) -> "Generators":
+    def from_affine_bytes(cls, curve: int, data: bytes, table: bool = False, window_bits: int = 0,
+                          raw_jacobian: bool = False) -> "Generators":
         if len(data) % AFFINE_BYTES:
             raise ValueError("affine point array must be a multiple of 72 bytes")
         lib = _lib.load()
         h = ctypes.c_void_p()
+        flags = (GENS_TABLE if table else 0) | (GENS_RAW_JACOBIAN if raw_jacobian else 0)
         _lib.check(lib.vdfgpu_gens_create(curve, _lib.as_ptr(data), len(data) // AFFINE_BYTES,
-                                          GENS_TABLE if table else 0, window_bits, ctypes.byref(h)))
+                                          flags, window_bits, ctypes.byref(h)))
         return cls(curve, h.value)
 
     @classmethod
@@ -35,13 +38,15 @@ class Generators:
         return cls.from_affine_bytes(curve, affines_to_bytes(pts, CURVE_BASE[curve]), **kw)
 
     @classmethod
-    def progression(cls, curve: int, k0: int, d: int, n: int, table: bool = False, window_bits: int = 0) -> "Generators":
+    def progression(cls, curve: int, k0: int, d: int, n: int, table: bool = False, window_bits: int = 0,
+                    raw_jacobian: bool = False) -> "Generators":
         """Synthetic known-discrete-log set P_i = (k0 + i d) G, generated on the device."""
         lib = _lib.load()
         h = ctypes.c_void_p()
+        flags = (GENS_TABLE if table else 0) | (GENS_RAW_JACOBIAN if raw_jacobian else 0)
         _lib.check(lib.vdfgpu_gens_progression(curve, _lib.as_ptr(k0.to_bytes(32, "little")),
                                                _lib.as_ptr(d.to_bytes(32, "little")), n,
-                                               GENS_TABLE if table else 0, window_bits, ctypes.byref(h)))
+                                               flags, window_bits, ctypes.byref(h)))
         return cls(curve, h.value)
 
     def __len__(self) -> int:

@@ -150,7 +150,9 @@ class RunningProver:
         cW, cT = bytearray(POINT_BYTES), bytearray(POINT_BYTES)
         _lib.check(lib.vdfgpu_running_commit(self._h, _lib.as_ptr(W2), _lib.as_ptr(X2), _lib.as_ptr(cW), _lib.as_ptr(cT)))
         if r is None:
-            r = challenge(bytes(cW), bytes(cT))
+            # the transcript absorbs canonical (affine) encodings, as nova's RO does via to_affine()
+            base = CURVE_BASE[self.gens.curve]
+            r = challenge(*[affine_to_bytes(point_from_bytes(bytes(c), base), base) for c in (cW, cT)])
         _lib.check(lib.vdfgpu_running_finish(self._h, _lib.as_ptr(fe_to_bytes(r, self.shape.m))))
         return bytes(cW), bytes(cT), r
 
