@@ -221,6 +221,85 @@ def r1cs_hbm_measurements(lib, _lib, torch, log2rows: int = 21):
     return res
 
 
+def cpu_fold_step(shape, W, X, sec_shape, sec_W, sec_X, gens, sec_gens, _lib):
+    from oracle import cpu_ref as C, pasta as O
+    cores = C.ncores()
+    lib = _lib.load()
+    parts = []
+    for curve, fid, m, sh, w, x, g in ((0, O.FIELD_FQ, O.Q, shape, W, X, gens), (1, O.FIELD_FP, O.P, sec_shape, sec_W, sec_X, sec_gens)):
+        ngen = max(sh.num_cons, sh.num_vars)
+        pts = bytearray(72 * ngen)
+        _lib.check(lib.vdfgpu_gens_export(g._h, 0, ngen, _lib.as_ptr(pts)))
+        parts.append((curve, fid, m, sh, O.fes_to_bytes(w, m), O.fes_to_bytes(x, m), bytes(pts), O.shape_to_coo_bytes(sh)))
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        for curve, fid, m, sh, wb, xb, pts, coo in parts:
+            one = O.fe_to_bytes(1, m)
+            abc1 = C.multiply_vec(fid, sh.num_cons, sh.num_vars, sh.num_io, coo, wb, one, xb)
+            abc2 = C.multiply_vec(fid, sh.num_cons, sh.num_vars, sh.num_io, coo, wb, one, xb)
+            T = C.cross_term(fid, sh.num_cons, abc1, abc2, one)
+            C.msm(curve, pts[:72 * sh.num_vars], wb, True, cores)
+            C.msm(curve, pts[:72 * sh.num_cons], T, True, cores)
+            r = O.fe_to_bytes(0x1234567890ABCDEF, m)
+            C.fold(fid, wb, wb, r)
+            C.fold(fid, T, T, r)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"fold_steps_per_s": 1.0 / best, "ms": best * 1e3, "cores": cores, "kind": "port"}
+
+
+def nova_step_measurements(_lib, ts=(1024, 4096, 16384)):
+    """GPU side of one Nova fold step (BASELINE config 3) = NIFS on the primary curve (Pallas; step circuit of t
+    inverse-MinRoot rounds + a SYNTHETIC 9.8k-constraint augmented block) followed by NIFS on the secondary curve
+    (Vesta; SYNTHETIC 10.3k-constraint block, the trivial step circuit): per curve the fresh witness goes H2D,
+    cross-term, ONE batched MSM for commit(W2) and commit(T), commitments D2H, fold with the challenge.  The four
+    commitments of the reference's step are covered; bellperson synthesis and the Poseidon RO (host) are not timed."""
+    from oracle import pasta as O           # input generation only (shapes + satisfying witnesses)
+    from vdf_b200 import msm as G, nova as N
+    res = {}
+    rng = O.XorShiftRng()
+    sec_shape, sec_W, sec_X, _ = O.make_step_instance(O.FIELD_FP, 0, O.State(1, 2, 3), aug_cons=10300)
+    sec_gs = N.R1CSShape(O.FIELD_FP, sec_shape.num_cons, sec_shape.num_vars, sec_shape.num_io, sec_shape.A, sec_shape.B, sec_shape.C)
+    sec_gens = G.Generators.progression(1, K0, D, max(sec_shape.num_cons, sec_shape.num_vars), table=True)
+    sec = N.RunningProver(sec_gs, sec_gens)
+    sec.set_running(sec_W, [0] * sec_shape.num_cons, N.RelaxedR1CSInstance(None, None, list(sec_X), 1))
+    sWb, sXb = O.fes_to_bytes(sec_W, O.P), O.fes_to_bytes(sec_X, O.P)
+    r_fixed = 0x1234567890ABCDEF
+    for t in ts:
+        state = O.State(O.field_random(rng, O.Q), O.field_random(rng, O.Q), t + 5)
+        shape, W, X, _ = O.make_step_instance(O.FIELD_FQ, t, state, aug_cons=9800)
+        gs = N.R1CSShape(O.FIELD_FQ, shape.num_cons, shape.num_vars, shape.num_io, shape.A, shape.B, shape.C)
+        gens = G.Generators.progression(0, K0, D, max(shape.num_cons, shape.num_vars), table=True)
+        pri = N.RunningProver(gs, gens)
+        pri.set_running(W, [0] * shape.num_cons, N.RelaxedR1CSInstance(None, None, list(X), 1))
+        Wb, Xb = O.fes_to_bytes(W, O.Q), O.fes_to_bytes(X, O.Q)
+
+        def step():
+            sec.prove_step_bytes(sWb, sXb, r_fixed)
+            pri.prove_step_bytes(Wb, Xb, r_fixed)
+
+        for _ in range(3):
+            step()
+        reps = 15
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            step()
+        dt = (time.perf_counter() - t0) / reps
+        res[str(t)] = {"fold_steps_per_s": 1.0 / dt, "ms": dt * 1e3, "primary_cons": shape.num_cons,
+                       "primary_vars": shape.num_vars, "secondary_cons": sec_shape.num_cons}
+        # CPU restatement of the same step's data-parallel work on the host cores (oracle/cpu_ref.c, "port"):
+        # 4 commitments (pasta-msm style Pippenger), 2 x 2 multiply_vec, cross-terms, folds
+        try:
+            res[str(t)]["cpu_port"] = cpu_fold_step(shape, W, X, sec_shape, sec_W, sec_X, gens, sec_gens, _lib)
+        except Exception as e:
+            res[str(t)]["cpu_port"] = {"error": repr(e)}
+        pri.close(); gens.close(); gs.close()
+    sec.close(); sec_gens.close(); sec_gs.close()
+    res["note"] = "GPU side only; augmented-circuit blocks are SYNTHETIC; host synthesis and Poseidon RO not timed"
+    return res
+
+
 def extra_measurements(lib, _lib, torch):
     """fold-steps/s (t = 1024, synthetic augmented block) and batched verify (C4)."""
     out = {}
@@ -276,6 +355,10 @@ def extra_measurements(lib, _lib, torch):
         prover.close(); gens.close(); gs.close()
     except Exception as e:  # side measurement: never lose the headline line
         out.setdefault("nifs_fold", {})["error"] = repr(e)
+    try:
+        out["nova_step"] = nova_step_measurements(_lib)
+    except Exception as e:
+        out["nova_step"] = {"error": repr(e)}
     try:
         out["r1cs_hbm"] = r1cs_hbm_measurements(lib, _lib, torch)
     except Exception as e:
