@@ -107,6 +107,11 @@ class Generators {
     ok_or_throw(vdfgpu_msm(h_, scalars.data(), scalars.size(), out.data()), "vdfgpu_msm");
     return out;
   }
+  // asynchronous pair for independent commitments: buffers must stay alive (ideally pinned) until wait(slot)
+  void commit_submit(const Fe* scalars, size_t n, Point* out, int slot) const {
+    ok_or_throw(vdfgpu_msm_submit(h_, scalars, n, out->data(), slot), "vdfgpu_msm_submit");
+  }
+  static void commit_wait(int slot) { ok_or_throw(vdfgpu_msm_wait(slot), "vdfgpu_msm_wait"); }
 
  private:
   int curve_;

@@ -87,6 +87,12 @@ int vdfgpu_gens_destroy(vdfgpu_gens* g);
 /* commit(v) = sum_i v_i * gens[i] over the first n generators; scalars in Montgomery form */
 int vdfgpu_msm(vdfgpu_gens* g, const void* scalars32_host, size_t n, void* out_point96_host);
 int vdfgpu_msm_dev(vdfgpu_gens* g, const void* scalars32_dev, size_t n, void* out_point96_dev);
+/* Asynchronous form of vdfgpu_msm for callers with several independent commitments: submit returns once the
+ * work is enqueued (use pinned host memory), wait blocks until out_point96_host of that slot is written.  The
+ * upload of slot k+1 overlaps the kernels of slot k.  slot in [0, 4); a busy slot must be waited before reuse;
+ * host buffers of a slot stay owned by the library until its wait returns. */
+int vdfgpu_msm_submit(vdfgpu_gens* g, const void* scalars32_host, size_t n, void* out_point96_host, int slot);
+int vdfgpu_msm_wait(int slot);
 /* k <= 4 scalar vectors (lengths lens[j]) over the same generators in ONE pass: k commitments for the latency
  * of one MSM.  nova commits to W and T of one NIFS::prove with the same generators. */
 int vdfgpu_msm_batch_dev(vdfgpu_gens* g, const void* const* scalars32_dev, const size_t* lens, uint32_t k,

@@ -209,3 +209,31 @@ def test_raw_jacobian_output(gpu_lib, cid):
         assert raw != nrm and O.jac_from_bytes(cv, raw) == O.jac_from_bytes(cv, nrm) == cv.msm_known_dlog(sc, k0, d)
         assert O.fe_from_bytes(nrm[64:96], cv.base) == 1
         assert g_raw.commit_bytes(O.fes_to_bytes([0] * 10, cv.order)) == bytes(96)
+
+
+def test_msm_submit_wait(gpu_lib):
+    """Asynchronous host-scalar MSM: two slots in flight give the same bytes as the synchronous call; slot misuse
+    is reported."""
+    import torch
+
+    from vdf_b200 import VdfGpuError, _lib
+    cv = O.PALLAS
+    rng = O.XorShiftRng()
+    n, k0, d = 20000, 11, 3
+    g = G.Generators.progression(cv.cid, k0, d, n, table=True)
+    vecs = [rand_scalars(rng, cv.order, n), rand_scalars(rng, cv.order, n - 7), rand_scalars(rng, cv.order, 100)]
+    want = [g.commit_bytes(O.fes_to_bytes(v, cv.order)) for v in vecs]
+    hosts = [torch.frombuffer(bytearray(O.fes_to_bytes(v, cv.order)), dtype=torch.uint8).pin_memory() for v in vecs]
+    outs = [torch.zeros(96, dtype=torch.uint8).pin_memory() for _ in vecs]
+    _lib.check(gpu_lib.vdfgpu_msm_submit(g._h, hosts[0].data_ptr(), len(vecs[0]), outs[0].data_ptr(), 0))
+    _lib.check(gpu_lib.vdfgpu_msm_submit(g._h, hosts[1].data_ptr(), len(vecs[1]), outs[1].data_ptr(), 1))
+    assert gpu_lib.vdfgpu_msm_submit(g._h, hosts[2].data_ptr(), len(vecs[2]), outs[2].data_ptr(), 1) == -3  # busy
+    _lib.check(gpu_lib.vdfgpu_msm_wait(0))
+    _lib.check(gpu_lib.vdfgpu_msm_submit(g._h, hosts[2].data_ptr(), len(vecs[2]), outs[2].data_ptr(), 0))
+    _lib.check(gpu_lib.vdfgpu_msm_wait(1))
+    _lib.check(gpu_lib.vdfgpu_msm_wait(0))
+    assert [bytes(o.numpy().tobytes()) for o in outs] == want
+    with pytest.raises(VdfGpuError):
+        _lib.check(gpu_lib.vdfgpu_msm_wait(0))      # nothing in flight
+    with pytest.raises(VdfGpuError):
+        _lib.check(gpu_lib.vdfgpu_msm_submit(g._h, hosts[0].data_ptr(), n, outs[0].data_ptr(), 9))

@@ -39,6 +39,8 @@ PROTOTYPES = {
     "vdfgpu_gens_window_bits": (c_uint32, [c_void_p, c_size_t]),
     "vdfgpu_gens_destroy": (c_int, [c_void_p]),
     "vdfgpu_msm": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vdfgpu_msm_submit": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_int]),
+    "vdfgpu_msm_wait": (c_int, [c_int]),
     "vdfgpu_msm_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "vdfgpu_msm_batch_dev": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_size_t), c_uint32, c_void_p]),
     "vdfgpu_msm_range_dev": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),

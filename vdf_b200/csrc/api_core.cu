@@ -312,6 +312,13 @@ int vdfgpu_shutdown(void) {
     for (auto& e : c.chunk_ev) { if (e) cudaEventDestroy(e); e = nullptr; }
     if (c.start_ev) cudaEventDestroy(c.start_ev);
     c.start_ev = nullptr;
+    for (auto& sl : c.slots) {
+      if (sl.copied) cudaEventDestroy(sl.copied);
+      if (sl.done) cudaEventDestroy(sl.done);
+      if (sl.d_scalars) cudaFree(sl.d_scalars);
+      if (sl.d_out) cudaFree(sl.d_out);
+      sl = AsyncSlot();
+    }
     c.copy_stream = nullptr;
     c.own_stream = nullptr;
     c.stream = nullptr;
@@ -482,6 +489,50 @@ int vdfgpu_msm(vdfgpu_gens* g, const void* scalars32_host, size_t n, void* out_p
     }
     d2h(out_point96_host, res.p, sizeof(jac_t), c.stream);
     VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+  });
+}
+
+// Asynchronous host-scalar MSM: the upload of one call's scalars (copy stream) overlaps the kernels of the
+// previous call (compute stream).  A caller with several independent commitments keeps 2 slots in flight.
+int vdfgpu_msm_submit(vdfgpu_gens* g, const void* scalars32_host, size_t n, void* out_point96_host, int slot) {
+  return guarded([&] {
+    if (!g || !out_point96_host || (n && !scalars32_host)) throw ArgError("msm_submit: null pointer");
+    if (slot < 0 || slot >= VDF_ASYNC_SLOTS) throw ArgError("msm_submit: slot out of range");
+    if (n > g->n) throw ArgError("msm_submit: more scalars than generators");
+    require_ready();
+    Context& c = ctx();
+    AsyncSlot& s = c.slots[slot];
+    if (s.busy) throw StateError("msm_submit: slot still in flight (call vdfgpu_msm_wait first)");
+    if (!s.copied) {
+      VDF_CUDA_CHECK(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+      VDF_CUDA_CHECK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+      VDF_CUDA_CHECK(cudaMalloc((void**)&s.d_out, sizeof(jac_t)));
+    }
+    if (s.cap < n) {
+      if (s.d_scalars) VDF_CUDA_CHECK(cudaFree(s.d_scalars));
+      s.d_scalars = nullptr;
+      VDF_CUDA_CHECK(cudaMalloc((void**)&s.d_scalars, (n ? n : 1) * sizeof(fe)));
+      s.cap = n;
+    }
+    // the slot is idle, so nothing on the compute stream still reads its buffers
+    if (n) VDF_CUDA_CHECK(cudaMemcpyAsync(s.d_scalars, scalars32_host, n * 32, cudaMemcpyHostToDevice, c.copy_stream));
+    VDF_CUDA_CHECK(cudaEventRecord(s.copied, c.copy_stream));
+    VDF_CUDA_CHECK(cudaStreamWaitEvent(c.stream, s.copied, 0));
+    msm_on_device(g, 0, s.d_scalars, n, s.d_out, true);
+    VDF_CUDA_CHECK(cudaMemcpyAsync(out_point96_host, s.d_out, sizeof(jac_t), cudaMemcpyDeviceToHost, c.stream));
+    VDF_CUDA_CHECK(cudaEventRecord(s.done, c.stream));
+    s.busy = true;
+  });
+}
+
+int vdfgpu_msm_wait(int slot) {
+  return guarded([&] {
+    if (slot < 0 || slot >= VDF_ASYNC_SLOTS) throw ArgError("msm_wait: slot out of range");
+    require_ready();
+    AsyncSlot& s = ctx().slots[slot];
+    if (!s.busy) throw StateError("msm_wait: nothing in flight in this slot");
+    VDF_CUDA_CHECK(cudaEventSynchronize(s.done));
+    s.busy = false;
   });
 }
 

@@ -20,6 +20,16 @@ struct StateError : std::runtime_error {
   using std::runtime_error::runtime_error;
 };
 
+// one in-flight host-scalar MSM of the asynchronous API (vdfgpu_msm_submit / vdfgpu_msm_wait)
+struct AsyncSlot {
+  fe* d_scalars = nullptr;
+  size_t cap = 0;
+  jac_t* d_out = nullptr;
+  cudaEvent_t copied = nullptr, done = nullptr;
+  bool busy = false;
+};
+constexpr int VDF_ASYNC_SLOTS = 4;
+
 struct Context {
   std::mutex mu;          // serialises library calls (re-entrant use from several host threads)
   bool ready = false;
@@ -29,6 +39,7 @@ struct Context {
   cudaStream_t copy_stream = nullptr;       // H2D of scalar chunks, overlapped with compute (vdfgpu_msm)
   cudaEvent_t chunk_ev[8] = {};             // chunk k of the scalars has arrived
   cudaEvent_t start_ev = nullptr;
+  AsyncSlot slots[VDF_ASYNC_SLOTS];
   uint64_t launches = 0;
   StageProfile prof;      // stage timing of the most recent MSM (vdfgpu_profile_*)
 };
