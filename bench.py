@@ -500,11 +500,12 @@ def run_ours(args):
     def finish(slot):
         _lib.check(lib.vdfgpu_msm_wait(slot))
         if world > 1:
+            # combine this step's partials; enqueued behind the MSM already submitted for the next step and
+            # read back asynchronously (the closing barrier + synchronize of the timed region covers it)
             out_dev.copy_(outs[slot], non_blocking=True)
             dist.all_gather_into_tensor(gathered, out_dev)
             _lib.check(lib.vdfgpu_point_sum_dev(0, gathered.data_ptr(), world, total_dev.data_ptr()))
-            out_host.copy_(total_dev)
-            torch.cuda.synchronize()
+            out_host.copy_(total_dev, non_blocking=True)
 
     def pipelined(k_steps):
         _lib.check(lib.vdfgpu_msm_submit(gens._h, scal_host.data_ptr(), n, outs[0].data_ptr(), 0))
