@@ -222,25 +222,29 @@ def r1cs_hbm_measurements(lib, _lib, torch, log2rows: int = 21):
 
 
 def cpu_fold_step(shape, W, X, sec_shape, sec_W, sec_X, gens, sec_gens, _lib):
+    """CPU baseline leg: the same step through oracle/cpu_ref.c on all host cores."""
     from oracle import cpu_ref as C, pasta as O
     cores = C.ncores()
     lib = _lib.load()
     parts = []
-    for curve, fid, m, sh, w, x, g in ((0, O.FIELD_FQ, O.Q, shape, W, X, gens), (1, O.FIELD_FP, O.P, sec_shape, sec_W, sec_X, sec_gens)):
-        ngen = max(sh.num_cons, sh.num_vars)
+    for curve, sh, w, x, g in ((0, shape, W, X, gens), (1, sec_shape, sec_W, sec_X, sec_gens)):
+        fid, cons, nvars, io, A, B, Cm = sh
+        m = O.MODULUS[fid]
+        ngen = max(cons, nvars)
         pts = bytearray(72 * ngen)
         _lib.check(lib.vdfgpu_gens_export(g._h, 0, ngen, _lib.as_ptr(pts)))
-        parts.append((curve, fid, m, sh, O.fes_to_bytes(w, m), O.fes_to_bytes(x, m), bytes(pts), O.shape_to_coo_bytes(sh)))
+        coo = O.shape_to_coo_bytes(O.R1CSShape(m, cons, nvars, io, A, B, Cm))
+        parts.append((curve, fid, m, cons, nvars, io, O.fes_to_bytes(w, m), O.fes_to_bytes(x, m), bytes(pts), coo))
     best = None
     for _ in range(2):
         t0 = time.perf_counter()
-        for curve, fid, m, sh, wb, xb, pts, coo in parts:
+        for curve, fid, m, cons, nvars, io, wb, xb, pts, coo in parts:
             one = O.fe_to_bytes(1, m)
-            abc1 = C.multiply_vec(fid, sh.num_cons, sh.num_vars, sh.num_io, coo, wb, one, xb)
-            abc2 = C.multiply_vec(fid, sh.num_cons, sh.num_vars, sh.num_io, coo, wb, one, xb)
-            T = C.cross_term(fid, sh.num_cons, abc1, abc2, one)
-            C.msm(curve, pts[:72 * sh.num_vars], wb, True, cores)
-            C.msm(curve, pts[:72 * sh.num_cons], T, True, cores)
+            abc1 = C.multiply_vec(fid, cons, nvars, io, coo, wb, one, xb)
+            abc2 = C.multiply_vec(fid, cons, nvars, io, coo, wb, one, xb)
+            T = C.cross_term(fid, cons, abc1, abc2, one)
+            C.msm(curve, pts[:72 * nvars], wb, True, cores)
+            C.msm(curve, pts[:72 * cons], T, True, cores)
             r = O.fe_to_bytes(0x1234567890ABCDEF, m)
             C.fold(fid, wb, wb, r)
             C.fold(fid, T, T, r)
@@ -255,25 +259,24 @@ def nova_step_measurements(_lib, ts=(1024, 4096, 16384)):
     (Vesta; SYNTHETIC 10.3k-constraint block, the trivial step circuit): per curve the fresh witness goes H2D,
     cross-term, ONE batched MSM for commit(W2) and commit(T), commitments D2H, fold with the challenge.  The four
     commitments of the reference's step are covered; bellperson synthesis and the Poseidon RO (host) are not timed."""
-    from oracle import pasta as O           # input generation only (shapes + satisfying witnesses)
-    from vdf_b200 import msm as G, nova as N
+    from vdf_b200 import encoding as E, msm as G, nova as N, synthetic as S   # inputs: package-side generator
     res = {}
-    rng = O.XorShiftRng()
-    sec_shape, sec_W, sec_X, _ = O.make_step_instance(O.FIELD_FP, 0, O.State(1, 2, 3), aug_cons=10300)
-    sec_gs = N.R1CSShape(O.FIELD_FP, sec_shape.num_cons, sec_shape.num_vars, sec_shape.num_io, sec_shape.A, sec_shape.B, sec_shape.C)
-    sec_gens = G.Generators.progression(1, K0, D, max(sec_shape.num_cons, sec_shape.num_vars), table=True)
+    s_cons, s_vars, s_io, sA, sB, sC, sec_W, sec_X = S.step_instance(E.FP, 0, 10300, seed=7)
+    sec_gs = N.R1CSShape(E.FP, s_cons, s_vars, s_io, sA, sB, sC)
+    sec_gens = G.Generators.progression(1, K0, D, max(s_cons, s_vars), table=True)
     sec = N.RunningProver(sec_gs, sec_gens)
-    sec.set_running(sec_W, [0] * sec_shape.num_cons, N.RelaxedR1CSInstance(None, None, list(sec_X), 1))
-    sWb, sXb = O.fes_to_bytes(sec_W, O.P), O.fes_to_bytes(sec_X, O.P)
+    sec.set_running(sec_W, [0] * s_cons, N.RelaxedR1CSInstance(None, None, list(sec_X), 1))
+    sWb, sXb = E.fes_to_bytes(sec_W, E.P), E.fes_to_bytes(sec_X, E.P)
+    sec_shape = (E.FP, s_cons, s_vars, s_io, sA, sB, sC)
     r_fixed = 0x1234567890ABCDEF
     for t in ts:
-        state = O.State(O.field_random(rng, O.Q), O.field_random(rng, O.Q), t + 5)
-        shape, W, X, _ = O.make_step_instance(O.FIELD_FQ, t, state, aug_cons=9800)
-        gs = N.R1CSShape(O.FIELD_FQ, shape.num_cons, shape.num_vars, shape.num_io, shape.A, shape.B, shape.C)
-        gens = G.Generators.progression(0, K0, D, max(shape.num_cons, shape.num_vars), table=True)
+        cons, nvars, io, A, B, C, W, X = S.step_instance(E.FQ, t, 9800, seed=42)
+        shape = (E.FQ, cons, nvars, io, A, B, C)
+        gs = N.R1CSShape(E.FQ, cons, nvars, io, A, B, C)
+        gens = G.Generators.progression(0, K0, D, max(cons, nvars), table=True)
         pri = N.RunningProver(gs, gens)
-        pri.set_running(W, [0] * shape.num_cons, N.RelaxedR1CSInstance(None, None, list(X), 1))
-        Wb, Xb = O.fes_to_bytes(W, O.Q), O.fes_to_bytes(X, O.Q)
+        pri.set_running(W, [0] * cons, N.RelaxedR1CSInstance(None, None, list(X), 1))
+        Wb, Xb = E.fes_to_bytes(W, E.Q), E.fes_to_bytes(X, E.Q)
 
         def step():
             sec.prove_step_bytes(sWb, sXb, r_fixed)
@@ -286,8 +289,8 @@ def nova_step_measurements(_lib, ts=(1024, 4096, 16384)):
         for _ in range(reps):
             step()
         dt = (time.perf_counter() - t0) / reps
-        res[str(t)] = {"fold_steps_per_s": 1.0 / dt, "ms": dt * 1e3, "primary_cons": shape.num_cons,
-                       "primary_vars": shape.num_vars, "secondary_cons": sec_shape.num_cons}
+        res[str(t)] = {"fold_steps_per_s": 1.0 / dt, "ms": dt * 1e3, "primary_cons": cons,
+                       "primary_vars": nvars, "secondary_cons": s_cons}
         # CPU restatement of the same step's data-parallel work on the host cores (oracle/cpu_ref.c, "port"):
         # 4 commitments (pasta-msm style Pippenger), 2 x 2 multiply_vec, cross-terms, folds
         try:
@@ -303,20 +306,16 @@ def nova_step_measurements(_lib, ts=(1024, 4096, 16384)):
 def extra_measurements(lib, _lib, torch):
     """fold-steps/s (t = 1024, synthetic augmented block) and batched verify (C4)."""
     out = {}
-    from oracle import pasta as O           # builds the synthetic step shape + witness (input generation)
-    from vdf_b200 import msm as G, nova as N
+    from vdf_b200 import encoding as E, msm as G, nova as N, synthetic as S
     try:
         t, aug = 1024, 9800
-        ovdf = O.PallasVDF()
-        rng = O.XorShiftRng()
-        res = O.State(O.field_random(rng, O.Q), O.field_random(rng, O.Q), t + 5)
-        shape, W, X, _ = O.make_step_instance(O.FIELD_FQ, t, res, aug_cons=aug)
-        gs = N.R1CSShape(O.FIELD_FQ, shape.num_cons, shape.num_vars, shape.num_io, shape.A, shape.B, shape.C)
-        ngen = max(shape.num_cons, shape.num_vars)
+        cons, nvars, io, A, B, C, W, X = S.step_instance(E.FQ, t, aug, seed=42)
+        gs = N.R1CSShape(E.FQ, cons, nvars, io, A, B, C)
+        ngen = max(cons, nvars)
         gens = G.Generators.progression(0, K0, D, ngen, table=True)
         prover = N.RunningProver(gs, gens)
-        Wb, Xb = O.fes_to_bytes(W, O.Q), O.fes_to_bytes(X, O.Q)
-        prover.set_running(W, [0] * shape.num_cons, N.RelaxedR1CSInstance(None, None, list(X), 1))
+        Wb, Xb = E.fes_to_bytes(W, E.Q), E.fes_to_bytes(X, E.Q)
+        prover.set_running(W, [0] * cons, N.RelaxedR1CSInstance(None, None, list(X), 1))
         r_fixed = 0x1234567890ABCDEF                # the random oracle is host work outside this path: fixed challenge
         for _ in range(3):
             prover.prove_step_bytes(Wb, Xb, r_fixed)
@@ -327,7 +326,7 @@ def extra_measurements(lib, _lib, torch):
         dt = (time.perf_counter() - t0) / reps
         out["nifs_fold"] = {
             "value": 1.0 / dt, "unit": "NIFS folds/s (one curve: commit(W2) + commit_T + fold, host witness in)",
-            "ms": dt * 1e3, "t": t, "cons": shape.num_cons, "vars": shape.num_vars, "nnz": gs.nnz,
+            "ms": dt * 1e3, "t": t, "cons": cons, "vars": nvars, "nnz": gs.nnz,
             "window_bits": gens.window_bits(ngen),
             "note": "augmented-circuit block is SYNTHETIC (9.8k random constraints); synthesis and the Poseidon RO stay on the host and are not timed"}
         prover.close(); gens.close()
@@ -335,10 +334,10 @@ def extra_measurements(lib, _lib, torch):
         # to_affine() normalises on the host): skips the single-thread inversion at the end of the MSM
         gens = G.Generators.progression(0, K0, D, ngen, table=True, raw_jacobian=True)
         prover = N.RunningProver(gs, gens)
-        prover.set_running(W, [0] * shape.num_cons, N.RelaxedR1CSInstance(None, None, list(X), 1))
+        prover.set_running(W, [0] * cons, N.RelaxedR1CSInstance(None, None, list(X), 1))
         lib_ = _lib.load()
         cW, cT = bytearray(96), bytearray(96)
-        rb = O.fe_to_bytes(0x1234567890ABCDEF, O.Q)
+        rb = E.fe_to_bytes(0x1234567890ABCDEF, E.Q)
 
         def raw_step():
             _lib.check(lib_.vdfgpu_running_commit(prover._h, _lib.as_ptr(Wb), _lib.as_ptr(Xb), _lib.as_ptr(cW), _lib.as_ptr(cT)))

@@ -22,7 +22,8 @@
  * Memory: "host" pointers are ordinary host memory owned by the caller for the duration of the call
  * (pinned memory makes the copies faster); "_dev" entry points take device pointers and enqueue on the
  * library stream (vdfgpu_set_stream) without synchronising.  Handles are owned by the library and freed
- * by the matching *_destroy.  Calls on one thread are ordered; the library keeps no pointer after return.
+ * by the matching *_destroy.  Calls on one thread are ordered; the library keeps no pointer after return
+ * (except vdfgpu_msm_submit, whose buffers it owns until vdfgpu_msm_wait of that slot).
  */
 #ifndef VDFGPU_H
 #define VDFGPU_H

@@ -155,3 +155,15 @@ def test_golden_vectors():
     T = shape.cross_term(W1, int(rec["u1"], 16), X1, W2, X2)
     import hashlib
     assert hashlib.sha256(O.fes_to_bytes(T, vdf.m)).hexdigest() == rec["T_sha256"]
+
+
+def test_package_synthetic_generator_matches_oracle_semantics():
+    """vdf_b200.synthetic (bench.py's input generator, kept outside oracle/) builds instances the oracle accepts."""
+    from vdf_b200 import synthetic as S
+    for fid in (O.FIELD_FP, O.FIELD_FQ):
+        cons, nv, io, A, B, C, W, X = S.step_instance(fid, 12, 60)
+        sh = O.R1CSShape(O.MODULUS[fid], cons, nv, io, A, B, C)
+        assert cons == 3 * 12 + 1 + 60 and sh.is_sat_relaxed(W, [0] * cons, 1, X)
+        vdf = O.MinRootVDF(fid)
+        s = vdf.inverse_eval(O.State(W[-4 * 12 - 4], W[-4 * 12 - 3], W[-4 * 12 - 2]), 12)
+        assert (W[-5], W[-2], W[-1]) == (s.x, s.y, s.i)      # last round's new_x, new_y and final_i
