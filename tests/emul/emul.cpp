@@ -35,6 +35,8 @@ void field_op(int op, const fe* a, const fe* b, fe* out, size_t n) {
   }
 }
 
+uint32_t g_affine_rounds = 0, g_affine_K = 8;   // set by emul_set_affine
+
 MsmPlan plan_for(size_t n, size_t stride, int table, uint32_t c, uint32_t S, uint32_t G, uint32_t logm, int is_mont) {
   MsmPlan p;
   p.n = (uint32_t)n;
@@ -51,12 +53,21 @@ MsmPlan plan_for(size_t n, size_t stride, int table, uint32_t c, uint32_t S, uin
   p.batch = 1;
   p.len[0] = (uint32_t)n;
   p.raw_jacobian = 0;
+  p.affine_rounds = g_affine_rounds;
+  p.affine_K = g_affine_K;
   return p;
 }
 
 }  // namespace
 
 extern "C" {
+
+// batched-affine halving rounds (msm_affine.cuh) for every following emul_msm* call; 0 = off
+int emul_set_affine(uint32_t rounds, uint32_t K) {
+  g_affine_rounds = rounds;
+  g_affine_K = K ? K : 8;
+  return 0;
+}
 
 int emul_field_op(int field, int op, const void* a, const void* b, void* out, size_t n) {
   if (field == 0) field_op<Fp>(op, (const fe*)a, (const fe*)b, (fe*)out, n);

@@ -214,3 +214,35 @@ def test_minroot_step_witness(emul, fid):
     for k, s in enumerate(res):
         _, W, _, _ = O.make_step_instance(fid, t, s)
         assert got[k * (4 * t + 1):(k + 1) * (4 * t + 1)] == W[3:]   # W = [x, y, i | step variables]
+
+
+@pytest.mark.parametrize("table", [0, 1])
+def test_msm_affine_rounds(emul, table):
+    """Batched-affine halving rounds (msm_affine.cuh) in front of the XYZZ accumulation: same result for any
+    number of rounds, including the exceptional pairs (equal points -> doubling, P + (-P), identity operands)."""
+    cv = O.PALLAS
+    rng, py = O.XorShiftRng(), random.Random(7)
+    n = 300
+    pts = cv.progression(5, 11, n)
+    sc = rand_scalars(rng, cv.order, n)
+    sc[0], sc[1], sc[2] = 0, 1, cv.order - 1
+    pts[7] = None                                      # identity operand
+    for k in range(20, 40):                             # a run of equal points with equal scalars: doublings,
+        pts[k], sc[k] = pts[20], sc[20]                 # then sums that meet again in later rounds
+    for k in range(40, 50, 2):                          # P + (-P) in the same bucket
+        pts[k + 1], sc[k + 1] = cv.neg(pts[k]), sc[k]
+    want = O.jac_to_bytes(cv, cv.msm(sc, pts))
+    skew = nova_like_scalars(py, rng, cv.order, n)
+    want_skew = O.jac_to_bytes(cv, cv.msm(skew, pts))
+    try:
+        for rounds, K in ((1, 8), (2, 3), (3, 64), (6, 5), (2, 1)):
+            emul.emul_set_affine(rounds, K)
+            for c, S in ((4, 5), (7, 16), (11, 33)):
+                assert _msm(emul, 0, table, c, S, 4, 2, pts, sc) == want, (rounds, K, c, S)
+            assert _msm(emul, 0, table, 6, 4, 4, 2, pts, skew) == want_skew, (rounds, K)
+        emul.emul_set_affine(2, 4)
+        assert _msm(emul, 0, table, 5, 8, 4, 2, [pts[4]] * 64, [12345] * 64) == O.jac_to_bytes(cv, cv.mul(12345 * 64, pts[4]))
+        assert _msm(emul, 0, table, 8, 16, 4, 3, pts[:1], [5]) == O.jac_to_bytes(cv, cv.mul(5, pts[0]))
+        assert _msm(emul, 0, table, 8, 16, 4, 3, pts[:1], [0]) == bytes(96)
+    finally:
+        emul.emul_set_affine(0, 0)

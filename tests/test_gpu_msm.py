@@ -195,6 +195,44 @@ def test_msm_host_chunked_overlap(gpu_lib, table, monkeypatch):
 
 
 @pytest.mark.parametrize("cid", CURVES)
+@pytest.mark.parametrize("table", [False, True])
+def test_msm_affine_rounds(gpu_lib, cid, table, monkeypatch):
+    """Optional batched-affine halving rounds in front of the XYZZ accumulation (msm_affine.cuh, off by default):
+    identical bytes for any number of rounds, on uniform and Nova-like scalars and on exceptional pairs."""
+    cv = O.CURVES[cid]
+    rng, py = O.XorShiftRng(), random.Random(11 + cid)
+    n, k0, d = 1 << 16, 5, 9
+    g = G.Generators.progression(cid, k0, d, n, table=table, window_bits=9)   # ~250+ entries per bucket
+    uni = O.fes_to_bytes([py.randrange(cv.order) for _ in range(n)], cv.order)
+    skew_sc = nova_like_scalars(py, rng, cv.order, n)
+    skew = O.fes_to_bytes(skew_sc, cv.order)
+    monkeypatch.setenv("VDFGPU_MSM_AFFINE", "0")
+    want_uni, want_skew = g.commit_bytes(uni), g.commit_bytes(skew)
+    assert O.jac_from_bytes(cv, want_skew) == cv.msm_known_dlog(skew_sc, k0, d)
+    for rounds, K in (("1", "64"), ("3", "7"), ("5", "32")):
+        monkeypatch.setenv("VDFGPU_MSM_AFFINE", rounds)
+        monkeypatch.setenv("VDFGPU_MSM_AFFINE_K", K)
+        assert g.commit_bytes(uni) == want_uni, (rounds, K)
+        assert g.commit_bytes(skew) == want_skew, (rounds, K)
+    g.close()
+    # equal points (doublings in every round), P + (-P), identity generators
+    m = 2000
+    pts = cv.progression(3, 1, 8) * (m // 8)
+    pts[5] = None
+    for k in range(16, 64, 2):
+        pts[k + 1] = cv.neg(pts[k])
+    sc = [12345] * m
+    g = G.Generators.from_points(cid, pts, table=table, window_bits=6)
+    monkeypatch.setenv("VDFGPU_MSM_AFFINE", "0")
+    want = g.commit_bytes(O.fes_to_bytes(sc, cv.order))
+    assert want == O.jac_to_bytes(cv, cv.msm(sc, pts))
+    monkeypatch.setenv("VDFGPU_MSM_AFFINE", "4")
+    monkeypatch.setenv("VDFGPU_MSM_AFFINE_K", "8")
+    assert g.commit_bytes(O.fes_to_bytes(sc, cv.order)) == want
+    g.close()
+
+
+@pytest.mark.parametrize("cid", CURVES)
 def test_raw_jacobian_output(gpu_lib, cid):
     """VDFGPU_GENS_RAW_JACOBIAN: the un-normalised (X, Y, Z) result is the same group element (what pasta-msm returns
     is un-normalised too); identity stays (0, 0, 0)."""

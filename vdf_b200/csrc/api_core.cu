@@ -82,6 +82,14 @@ static MsmPlan make_plan(const vdfgpu_gens* g, size_t n, bool is_mont, uint32_t 
   p.logm = 3;
   if (const char* s = std::getenv("VDFGPU_MSM_G")) p.G = (uint32_t)std::atoi(s);
   if (const char* s = std::getenv("VDFGPU_MSM_LOGM")) p.logm = (uint32_t)std::atoi(s);
+  // batched-affine halving rounds (msm_affine.cuh): worth their fixed costs only in the throughput regime and
+  // while the buckets still hold >= 16 entries on average
+  p.affine_rounds = 0;
+  p.affine_K = 64;
+  if (const char* s = std::getenv("VDFGPU_MSM_AFFINE")) p.affine_rounds = (uint32_t)std::atoi(s);
+  if (const char* s = std::getenv("VDFGPU_MSM_AFFINE_K")) p.affine_K = (uint32_t)std::atoi(s);
+  if (p.affine_K < 1) p.affine_K = 1;
+  if (E >= (1ull << 31)) p.affine_rounds = 0;   // list positions carry a flag in bit 31
   return p;
 }
 

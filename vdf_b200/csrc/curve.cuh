@@ -22,6 +22,7 @@ struct jac_t {  // pasta_curves Ep/Eq memory layout (X, Y, Z), identity <=> Z ==
 
 template <class F>
 struct Curve {
+  typedef F field;   // coordinate field
   static VDF_HD bool aff_is_inf(const affine_t& p) { return F::is_zero(p.x) && F::is_zero(p.y); }
   static VDF_HD bool is_inf(const xyzz_t& p) { return F::is_zero(p.ZZ); }
 

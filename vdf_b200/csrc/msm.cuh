@@ -15,7 +15,9 @@
 //                to a record list, complete buckets are stored directly.
 //   5 fixup      segmented reduction of the record list (again range-based, log depth), then owners
 //                fold what is left.
-//   6 reduce     sum_j j*B_j by chunked running sums, recursively on the chunk totals.
+//   6 reduce     sum_j j*B_j.  Small sets: bit decomposition (row b = sum of the buckets whose index has bit
+//                b set, radix-4 tree sums, then 2^b applied per row in parallel).  Large sets: one level of
+//                chunk-local running sums, then the same bit decomposition over the chunk totals.
 //   7 final      tree sum of the partial results, Horner over windows (plain mode only), normalise to
 //                (x, y, 1) and write a pasta_curves Jacobian point.
 //
@@ -28,6 +30,7 @@
 #pragma once
 #include "curve.cuh"
 #include "launch.cuh"
+#include "msm_affine.cuh"
 
 namespace vdf {
 
@@ -46,6 +49,8 @@ struct MsmPlan {
   uint32_t batch = 1;      // independent scalar vectors over the SAME points (one result each), <= MSM_MAX_BATCH
   uint32_t len[4] = {0, 0, 0, 0};  // length of each vector (<= n); shorter vectors are zero-padded
   uint32_t raw_jacobian = 0;       // 1: write (X*ZZ, Y*ZZZ, ZZ) without the final inversion (caller normalises)
+  uint32_t affine_rounds = 0;      // batched-affine halving rounds before the XYZZ accumulation (msm_affine.cuh)
+  uint32_t affine_K = 64;          // additions per thread and round sharing one running product
 };
 
 constexpr uint32_t MSM_MAX_BATCH = 4;
@@ -163,17 +168,6 @@ struct RecHdr {
   uint32_t flags;   // REC_FIRST: piece starts the bucket; REC_LAST: piece ends it
 };
 
-VDF_HD uint32_t upper_bound_u32(const uint32_t* a, uint32_t n, uint32_t x) {
-  // first index with a[idx] > x
-  uint32_t lo = 0, hi = n;
-  while (lo < hi) {
-    uint32_t mid = lo + ((hi - lo) >> 1);
-    if (a[mid] <= x) lo = mid + 1;
-    else hi = mid;
-  }
-  return lo;
-}
-
 // Chunked MSMs: every chunk accumulates into its OWN zeroed bucket array with plain stores (an addition inside
 // the divergent flush path would serialise the warp), and this fully converged kernel folds it into the
 // running array afterwards: total[b] += chunk[b].
@@ -190,12 +184,14 @@ struct BucketMergeFn {
   }
 };
 
-template <class C>
+template <class C, bool DIRECT = false>   // DIRECT: the list holds the points themselves (after affine rounds)
 struct AccumulateFn {
   const uint32_t* offs;  // [NBK + 1]
   uint32_t NBK;
   const uint32_t* sref;
   const affine_t* pts;
+  const fe* xs;          // DIRECT: x and y of list position pos
+  const fe* ys;
   xyzz_t* buckets;       // [NBK], zero-initialised
   RecHdr* rec_hdr;       // [2 * threads]
   xyzz_t* rec_pt;
@@ -231,11 +227,17 @@ struct AccumulateFn {
         asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt));
       }
 #endif
-      uint32_t ref = sref[pos];
       affine_t pt;
-      const affine_t* src = pts + (ref & 0x7fffffffu);
-      pt.x = fe_load(&src->x);
-      pt.y = fe_load(&src->y);
+      uint32_t ref = 0;
+      if (DIRECT) {
+        pt.x = fe_load(xs + pos);
+        pt.y = fe_load(ys + pos);
+      } else {
+        ref = sref[pos];
+        const affine_t* src = pts + (ref & 0x7fffffffu);
+        pt.x = fe_load(&src->x);
+        pt.y = fe_load(&src->y);
+      }
       C::madd_signed_call(acc, pt, (ref >> 31) != 0);
     }
     flush(t, lo, b, bs, be, seg_start, hi, acc);
@@ -585,13 +587,31 @@ void msm_accumulate(L& L_, const MsmPlan& p, const affine_t* pts, const ScalarSe
   L_.mark(MSM_STAGE_SCATTER);
   L_.template run<256>((E + ScatterFn::PER - 1) / ScatterFn::PER, ScatterFn{keys, offs, fill, sref, p, E});
 
+  // optional batched-affine halving rounds (msm_affine.cuh): the list shrinks 2^rounds times
+  size_t e_cap = E;
+  fe *alist_x = nullptr, *alist_y = nullptr;
+  uint32_t* alist_offs = nullptr;
+  uint32_t S = p.S;
+  L_.mark(MSM_STAGE_ACCUMULATE);
+  if (p.affine_rounds) {
+    msm_affine_rounds<L, typename C::field>(L_, p.affine_rounds, p.affine_K, NBK, sref, pts, offs, e_cap, &alist_x,
+                                            &alist_y, &alist_offs);
+    size_t s2 = e_cap / (148 * 768);
+    if (s2 < 32) s2 = 32;
+    if (s2 < S) S = (uint32_t)s2;
+  }
+
   // accumulate over fixed-size ranges of the sorted list
-  size_t T_acc = (E + p.S - 1) / p.S;
+  size_t T_acc = (e_cap + S - 1) / S;
   size_t n_rec = 2 * T_acc;
   RecHdr* hdr_a = L_.template alloc<RecHdr>(n_rec);
   xyzz_t* pt_a = L_.template alloc<xyzz_t>(n_rec);
-  L_.mark(MSM_STAGE_ACCUMULATE);
-  L_.template run<128, 5>(T_acc, AccumulateFn<C>{offs, NBK, sref, pts, buckets, hdr_a, pt_a, p.S});
+  if (p.affine_rounds)
+    L_.template run<128, 5>(T_acc, AccumulateFn<C, true>{alist_offs, NBK, nullptr, nullptr, alist_x, alist_y, buckets,
+                                                         hdr_a, pt_a, S});
+  else
+    L_.template run<128, 5>(T_acc, AccumulateFn<C>{offs, NBK, sref, pts, nullptr, nullptr, buckets, hdr_a, pt_a, S});
+  L_.free(alist_x); L_.free(alist_offs);
 
   // segmented reduction of the records: log-depth levels, then owners
   RecHdr* hdr_b = nullptr;
