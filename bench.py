@@ -558,21 +558,33 @@ def run_ours(args):
     _lib.check(lib.vdfgpu_imad_peak(ctypes.byref(pw), ctypes.byref(pl), ctypes.byref(pa)))
     alg_mul32 = float(n) * W * FIELD_MUL_PER_MADD * MUL32_PER_FIELD_MUL
     acc_s = stage_ms["accumulate"] * 1e-3
+    R = gens.affine_rounds(n)
     traffic = None
     tfile = ROOT / "profiles" / "traffic.json"   # dram bytes of one accumulate launch from the committed ncu capture
     if tfile.exists():
         t = json.loads(tfile.read_text())
-        if t.get("log2n") == args.log2n and t.get("window_bits") == c_bits and t.get("layout") == ("table" if table else "plain"):
-            traffic = t["accumulate_dram_bytes_per_launch"]
+        if t.get("log2n") == args.log2n and t.get("window_bits") == c_bits and t.get("layout") == ("table" if table else "plain") \
+                and t.get("affine_rounds", 0) == R:
+            traffic = t.get("accumulate_stage_dram_bytes", t.get("accumulate_dram_bytes_per_launch"))
+    # field multiplications the accumulate stage really executes: R batched-affine halving rounds at 6 per addition
+    # (the list shrinks to ~E / 2^R), then the XYZZ mixed additions of what is left at 10
+    E = float(n) * W
+    left = E / (1 << R)
+    executed_mul = (E - left) * 6 + left * FIELD_MUL_PER_MADD
     roofline = {
-        "bound": "imad", "kernel": "AccumulateFn (XYZZ bucket accumulation)",
+        "bound": "imad",
+        "kernel": (f"accumulate stage = {R} batched-affine halving rounds (AffineFwdFn, BatchInvFn, AffineBwdFn) + "
+                   "AccumulateFn (XYZZ ranges)") if R else "AccumulateFn (XYZZ bucket accumulation)",
         "achieved": alg_mul32 / acc_s / 1e12, "peak": pw.value / 1e12, "unit": "Tmul32/s",
         "frac": (alg_mul32 / acc_s) / pw.value, "traffic": traffic,
-        "frac_executed": (float(n) * W * FIELD_MUL_PER_MADD * 88 / acc_s) / pw.value,
+        "frac_executed": (executed_mul * 88 / acc_s) / pw.value,
         "algorithmic": f"n * W(c) * 10 field-mul * 136 mul32 (SURVEY 8d) with the real c={c_bits}, W={W}",
         "peak_source": "measured in this run: vdfgpu_imad_peak, register-only IMAD.WIDE.U32.X carry chains with loop-variant "
                        "multiplicands (nominal 148 SM x 4 SMSP x 8 lanes x 1.965 GHz = 9.3 T; MEASURED_PEAKS.json has no integer figure)",
-        "frac_executed_note": "the specialised multiplier executes 88 products per field multiplication, the SURVEY convention counts 136",
+        "frac_executed_note": "products really executed: 88 per field multiplication (the SURVEY convention counts 136), 6 "
+                              "multiplications per affine addition and 10 per XYZZ addition; frac > 1 means the stage does "
+                              "less arithmetic than the convention assumes",
+        "affine_rounds": R,
         "imad_lo_per_s": pl.value, "iadd3_per_s": pa.value,
         "kernel_ms": stage_ms["accumulate"], "stage_ms": stage_ms,
         "share_of_step": stage_ms["accumulate"] / max(1e-9, sum(stage_ms.values())),

@@ -83,6 +83,8 @@ int vdfgpu_gens_progression(int curve, const void* k0_le32, const void* d_le32, 
 int vdfgpu_gens_export(const vdfgpu_gens* g, size_t first, size_t count, void* points_affine72_host);
 size_t vdfgpu_gens_len(const vdfgpu_gens* g);
 uint32_t vdfgpu_gens_window_bits(const vdfgpu_gens* g, size_t n);
+/* batched-affine halving rounds an n-scalar commitment over g runs before its XYZZ accumulation (measurement) */
+uint32_t vdfgpu_gens_affine_rounds(const vdfgpu_gens* g, size_t n);
 int vdfgpu_gens_destroy(vdfgpu_gens* g);
 
 /* commit(v) = sum_i v_i * gens[i] over the first n generators; scalars in Montgomery form */

@@ -18,7 +18,7 @@ ap.add_argument("--log2n", type=int, nargs="+", default=[16, 18, 20, 22])
 ap.add_argument("--layouts", nargs="+", default=["table", "plain"])
 ap.add_argument("--S", type=int, nargs="+", default=[0])
 ap.add_argument("--c", type=int, nargs="+", default=[0])
-ap.add_argument("--affine", type=int, nargs="+", default=[0], help="batched-affine halving rounds")
+ap.add_argument("--affine", type=int, nargs="+", default=[-1], help="batched-affine halving rounds (-1 = library default)")
 ap.add_argument("--K", type=int, nargs="+", default=[64], help="additions per thread and affine round")
 ap.add_argument("--reps", type=int, default=3)
 args = ap.parse_args()
@@ -38,8 +38,12 @@ for lg in args.log2n:
         for c in args.c:
             g = G.Generators.progression(0, 12345, 678, n, table=(layout == "table"), window_bits=c)
             for S, A, K in [(S, A, K) for S in args.S for A in args.affine for K in (args.K if A else args.K[:1])]:
-                os.environ["VDFGPU_MSM_AFFINE"] = str(A)
-                os.environ["VDFGPU_MSM_AFFINE_K"] = str(K)
+                if A >= 0:
+                    os.environ["VDFGPU_MSM_AFFINE"] = str(A)
+                    os.environ["VDFGPU_MSM_AFFINE_K"] = str(K)
+                else:
+                    os.environ.pop("VDFGPU_MSM_AFFINE", None)
+                    os.environ.pop("VDFGPU_MSM_AFFINE_K", None)
                 if S:
                     os.environ["VDFGPU_MSM_S"] = str(S)
                 else:
@@ -59,7 +63,7 @@ for lg in args.log2n:
                 buf = (ctypes.c_double * 7)()
                 _lib.check(lib.vdfgpu_profile_read(buf, 7))
                 _lib.check(lib.vdfgpu_profile_enable(0))
-                rec = {"log2n": lg, "layout": layout, "c": g.window_bits(n), "S": S, "affine": A, "K": K, "out": bytes(out.cpu().numpy()[:8]).hex(), "ms": round(total, 4),
+                rec = {"log2n": lg, "layout": layout, "c": g.window_bits(n), "S": S, "affine": g.affine_rounds(n) if A < 0 else A, "K": K, "out": bytes(out.cpu().numpy()[:8]).hex(), "ms": round(total, 4),
                        "Gpts/s": round(n / total / 1e6, 4), "stages": {k: round(v, 4) for k, v in zip(names, buf)}}
                 print(json.dumps(rec), flush=True)
             g.close()

@@ -37,6 +37,7 @@ PROTOTYPES = {
     "vdfgpu_gens_export": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p]),
     "vdfgpu_gens_len": (c_size_t, [c_void_p]),
     "vdfgpu_gens_window_bits": (c_uint32, [c_void_p, c_size_t]),
+    "vdfgpu_gens_affine_rounds": (c_uint32, [c_void_p, c_size_t]),
     "vdfgpu_gens_destroy": (c_int, [c_void_p]),
     "vdfgpu_msm": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "vdfgpu_msm_submit": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_int]),

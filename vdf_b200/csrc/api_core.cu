@@ -85,11 +85,19 @@ static MsmPlan make_plan(const vdfgpu_gens* g, size_t n, bool is_mont, uint32_t 
   // batched-affine halving rounds (msm_affine.cuh): worth their fixed costs only in the throughput regime and
   // while the buckets still hold >= 16 entries on average
   p.affine_rounds = 0;
-  p.affine_K = 64;
+  p.affine_K = 32;
+  if (E >= (1ull << 23) && E <= (1ull << 29)) {
+    // measured on B200 (profiles/r1_experiments.md): -3 % at 2^20 points, -5 % at 2^22, -9 % at 2^24.  Halve while
+    // a bucket keeps >= 12 entries on average and a round still has >= 4 M additions to pay for its fixed costs
+    // (three small launches + one inversion latency); the XYZZ ranges finish the rest
+    const size_t avg = E / ((size_t)p.NB * batch * p.B);
+    while (p.affine_rounds < 5 && (avg >> (p.affine_rounds + 1)) >= 12 && (E >> (p.affine_rounds + 1)) >= (4u << 20))
+      p.affine_rounds++;
+  }
   if (const char* s = std::getenv("VDFGPU_MSM_AFFINE")) p.affine_rounds = (uint32_t)std::atoi(s);
   if (const char* s = std::getenv("VDFGPU_MSM_AFFINE_K")) p.affine_K = (uint32_t)std::atoi(s);
   if (p.affine_K < 1) p.affine_K = 1;
-  if (E >= (1ull << 31)) p.affine_rounds = 0;   // list positions carry a flag in bit 31
+  if (E >= (1ull << 31)) p.affine_rounds = 0;   // 32-bit list positions, 0xffffffff reserved
   return p;
 }
 
@@ -471,6 +479,11 @@ size_t vdfgpu_gens_len(const vdfgpu_gens* g) { return g ? g->n : 0; }
 uint32_t vdfgpu_gens_window_bits(const vdfgpu_gens* g, size_t n) {
   if (!g) return 0;
   return (g->flags & VDFGPU_GENS_TABLE) ? g->c : msm_pick_c(n, false);
+}
+
+uint32_t vdfgpu_gens_affine_rounds(const vdfgpu_gens* g, size_t n) {
+  if (!g || n == 0 || n > g->n) return 0;
+  return make_plan(g, n, true).affine_rounds;
 }
 
 int vdfgpu_gens_destroy(vdfgpu_gens* g) {

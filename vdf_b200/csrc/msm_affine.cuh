@@ -231,6 +231,16 @@ struct AffineBwdFn {
   }
 };
 
+// Items per thread close to `guess` such that the grid is a whole number of waves (`wave` = threads resident on
+// the GPU at once): with only a few waves, a partly filled last wave costs as much as a full one.
+static inline uint32_t fit_waves(size_t items, uint32_t guess, size_t wave) {
+  if (guess < 1) guess = 1;
+  size_t waves = (items + (size_t)guess * wave / 2) / ((size_t)guess * wave);   // nearest
+  if (waves < 1) return guess;           // less than one wave of work: keep the parallelism
+  if (waves > 16) return guess;          // many waves: the tail no longer matters
+  return (uint32_t)((items + waves * wave - 1) / (waves * wave));
+}
+
 // upper bound of the list length after one round: sum ceil(s_b / 2) <= (sum s_b + buckets) / 2
 static inline size_t affine_round_cap(size_t e_in, size_t nbk) { return (e_in + nbk + 1) / 2; }
 
@@ -250,7 +260,8 @@ void msm_affine_rounds(L& L_, uint32_t rounds, uint32_t K, uint32_t NBK, const u
   uint32_t* cur_offs = nullptr;
   for (uint32_t r = 0; r < rounds; r++) {
     const size_t cap = affine_round_cap(e_cap, NBK);
-    const uint32_t T = (uint32_t)((cap + K - 1) / K);
+    const uint32_t Kr = fit_waves(cap, K, (size_t)148 * VDF_AFF_BWD_MINB * 128);   // backward pass: whole waves
+    const uint32_t T = (uint32_t)((cap + Kr - 1) / Kr);
     uint32_t* cnt = L_.template alloc<uint32_t>(NBK);
     uint32_t* offs_out = L_.template alloc<uint32_t>((size_t)NBK + 1);
     const size_t cap_pad = (cap + PairListFn::CH - 1) / PairListFn::CH * PairListFn::CH;
@@ -263,9 +274,9 @@ void msm_affine_rounds(L& L_, uint32_t rounds, uint32_t K, uint32_t NBK, const u
     L_.exclusive_scan(cnt, offs_out, NBK);
     L_.template run<128>((cap + PairListFn::CH - 1) / PairListFn::CH,
                          PairListFn{offs_in, offs_out, NBK, r == 0 ? sref : nullptr, ra, rb});
-    L_.template run<128>(T, AffineFwdFn<F>{in, ra, rb, offs_out + NBK, T, K, prefix, ptot});
+    L_.template run<128>(T, AffineFwdFn<F>{in, ra, rb, offs_out + NBK, T, Kr, prefix, ptot});
     L_.template run<64>((T + BatchInvFn<F>::J - 1) / BatchInvFn<F>::J, BatchInvFn<F>{ptot, T});
-    L_.template run<128, VDF_AFF_BWD_MINB>(T, AffineBwdFn<F>{in, ra, rb, offs_out + NBK, T, K, prefix, ptot, out,
+    L_.template run<128, VDF_AFF_BWD_MINB>(T, AffineBwdFn<F>{in, ra, rb, offs_out + NBK, T, Kr, prefix, ptot, out,
                                                              out + cap});
     L_.free(cnt); L_.free(refs); L_.free(prefix); L_.free(ptot);
     L_.free(cur); L_.free(cur_offs);

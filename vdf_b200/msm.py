@@ -55,6 +55,9 @@ class Generators:
     def window_bits(self, n: int) -> int:
         return _lib.load().vdfgpu_gens_window_bits(self._h, n)
 
+    def affine_rounds(self, n: int) -> int:
+        return _lib.load().vdfgpu_gens_affine_rounds(self._h, n)
+
     def export(self, first: int = 0, count: Optional[int] = None) -> List[Affine]:
         count = len(self) - first if count is None else count
         buf = bytearray(count * AFFINE_BYTES)
