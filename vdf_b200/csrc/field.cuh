@@ -417,6 +417,29 @@ VDF_HD fe fe_load(const void* p) {
   return r;
 }
 
+// Load for RANDOM 32 / 64-byte gathers (points picked by the sorted references): read-only path and the smallest
+// L2 prefetch size, so that a miss does not pull the neighbouring sectors of the 128-byte line from DRAM.
+#ifndef VDF_GATHER_L2
+#define VDF_GATHER_L2 64
+#endif
+VDF_HD fe fe_load_gather(const void* p) {
+#if defined(__CUDA_ARCH__) && VDF_GATHER_L2 > 0
+  fe r;
+#define VDF_STR2(x) #x
+#define VDF_STR(x) VDF_STR2(x)
+  asm volatile("ld.global.nc.L2::" VDF_STR(VDF_GATHER_L2) "B.v4.u32 {%0,%1,%2,%3}, [%8];\n\t"
+               "ld.global.nc.L2::" VDF_STR(VDF_GATHER_L2) "B.v4.u32 {%4,%5,%6,%7}, [%8+16];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+                 "=r"(r.v[7])
+               : "l"(p));
+#undef VDF_STR
+#undef VDF_STR2
+  return r;
+#else
+  return fe_load(p);
+#endif
+}
+
 VDF_HD void fe_store(void* p, const fe& a) {
 #if defined(__CUDA_ARCH__)
   uint4* q = reinterpret_cast<uint4*>(p);

@@ -235,8 +235,8 @@ struct AccumulateFn {
       } else {
         ref = sref[pos];
         const affine_t* src = pts + (ref & 0x7fffffffu);
-        pt.x = fe_load(&src->x);
-        pt.y = fe_load(&src->y);
+        pt.x = fe_load_gather(&src->x);
+        pt.y = fe_load_gather(&src->y);
       }
       C::madd_signed_call(acc, pt, (ref >> 31) != 0);
     }

@@ -37,15 +37,15 @@ struct PointSrc {
   const fe* xs;
   const fe* ys;
   VDF_HD fe x(uint32_t ref) const {
-    return aos ? fe_load(&aos[ref & 0x7fffffffu].x) : fe_load(xs + ref);
+    return aos ? fe_load_gather(&aos[ref & 0x7fffffffu].x) : fe_load(xs + ref);
   }
   template <class F>
   VDF_HD affine_t get(uint32_t ref) const {
     affine_t a;
     if (aos) {
       const affine_t* s = aos + (ref & 0x7fffffffu);
-      a.x = fe_load(&s->x);
-      a.y = fe_load(&s->y);
+      a.x = fe_load_gather(&s->x);
+      a.y = fe_load_gather(&s->y);
       if (ref >> 31) a.y = F::neg(a.y);   // -(0,0) = (0,0): the identity stays the identity
     } else {
       a.x = fe_load(xs + ref);
