@@ -178,7 +178,8 @@ int vdfgpu_point_sum_dev(int curve, const void* points96_dev, size_t k, void* ou
 
 /* ---- measurement helpers (bench.py) ------------------------------------------------------------------ */
 /* elementwise field multiply out[i] = a[i]*b[i] iterated `iters` times (out <- out*b): field-layer parity
- * tests and the integer-multiply roofline probe */
+ * tests and the integer-multiply roofline probe.  Bit 31 of iters: out-of-line multiplier; bit 30: dedicated
+ * squaring instead (out <- out^2, b unused) */
 int vdfgpu_field_mul_batch(int field, const void* a_host, const void* b_host, size_t n, uint32_t iters,
                            void* out_host);
 /* register-only integer-multiply peak probe: returns 32x32->64 products per second in *out */

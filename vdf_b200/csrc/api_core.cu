@@ -233,9 +233,13 @@ struct FieldMulFn {
   const fe* a; const fe* b; fe* out; uint32_t iters;
   VDF_HD void operator()(size_t i) const {
     fe x = fe_load(a + i), y = fe_load(b + i);
-    // bit 31 of iters selects the out-of-line multiplier (latency probe of the call overhead)
-    const uint32_t n_it = iters & 0x7fffffffu;
-    if (iters >> 31) {
+    // bit 31 of iters selects the out-of-line multiplier (latency probe of the call overhead), bit 30 the
+    // dedicated squaring (x <- x^2, b unused)
+    const uint32_t n_it = iters & 0x3fffffffu;
+    if (iters & 0x40000000u) {
+#pragma unroll 1
+      for (uint32_t k = 0; k < n_it; k++) x = F::sqr(x);
+    } else if (iters >> 31) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
       for (uint32_t k = 0; k < n_it; k++) x = F::mul_call(x, y);

@@ -122,10 +122,10 @@ struct Curve {
       else acc = identity();
       return;
     }
-    fe PP = F::mul_call(P, P);
+    fe PP = F::sqr_call(P);
     fe PPP = F::mul_call(P, PP);
     fe Q = F::mul_call(acc.X, PP);
-    fe X3 = F::sub(F::sub(F::mul_call(R, R), PPP), F::dbl(Q));
+    fe X3 = F::sub(F::sub(F::sqr_call(R), PPP), F::dbl(Q));
     fe Y3 = F::sub(F::mul_call(R, F::sub(Q, X3)), F::mul_call(acc.Y, PPP));
     acc.ZZ = F::mul_call(acc.ZZ, PP);
     acc.ZZZ = F::mul_call(acc.ZZZ, PPP);

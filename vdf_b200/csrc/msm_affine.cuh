@@ -208,7 +208,7 @@ struct AffineBwdFn {
         if (kind == PAIR_ZERO) { a.x = F::zero(); a.y = F::zero(); store(o, a); continue; }
         if (kind == PAIR_DBL) {
           d = F::dbl(a.y);
-          fe xx = F::mul(a.x, a.x);
+          fe xx = F::sqr(a.x);
           num = F::add(F::dbl(xx), xx);   // 3 x^2 (a = 0)
         } else {
           num = F::sub(b.y, a.y);
@@ -220,7 +220,7 @@ struct AffineBwdFn {
       inv = F::mul(inv, d);
       fe lam = F::mul(num, dinv);
       affine_t r;
-      r.x = F::sub(F::sub(F::mul(lam, lam), a.x), b.x);
+      r.x = F::sub(F::sub(F::sqr(lam), a.x), b.x);
       r.y = F::sub(F::mul(lam, F::sub(a.x, r.x)), a.y);
       store(o, r);
     }
