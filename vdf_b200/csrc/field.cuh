@@ -323,7 +323,7 @@ struct Field {
   // a^2 = sum_i a_i 2^(32 i) * V_i with V_i = a_i 2^(32 i) + 2 * sum_(j>i) a_j 2^(32 j): row i of the multiplication
   // above with the multiplicand V_i = [0 (j < i), a_i, (2a)_(i+1) & ~1, (2a)_(i+2), ...] and the products of its zero
   // limbs dropped -- 36 instead of 64 products, same interleaved reduction, no separate doubling pass (2a < 2^256).
-  // Validated carry-exact against big integers in scratch form before it ran on a GPU.
+  // tools/ptx_model.py replays these chains carry-exactly against big integers (tests/test_ptx_model.py).
   // shift_mad with the products of the ZO lowest odd limbs (all zero) replaced by carry propagation
   template <int ZO>
   static VDF_D void shift_mad_z(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_t bi) {
