@@ -180,6 +180,18 @@ def test_msm_batch(emul, table):
                                    ptr(lens), k, ptr(out)) == 0
         for j, v in enumerate(use):
             assert out.tobytes()[96 * j:96 * j + 96] == O.jac_to_bytes(cv, cv.msm_known_dlog(v, 8, 3)), (k, j)
+    # the same batch with batched-affine halving rounds in front of the accumulation
+    try:
+        emul.emul_set_affine(2, 5)
+        lens = np.array([len(v) for v in vecs], dtype=np.uint32)
+        sb = aligned(b"".join(O.fes_to_bytes(v, cv.order) for v in vecs))
+        out = np.zeros(96 * 4, np.uint8)
+        assert emul.emul_msm_batch(0, table, 5, 9, ptr(aligned(O.affines_to_bytes(cv, pts))), SZ(n), ptr(sb),
+                                   ptr(lens), 4, ptr(out)) == 0
+        for j, v in enumerate(vecs):
+            assert out.tobytes()[96 * j:96 * j + 96] == O.jac_to_bytes(cv, cv.msm_known_dlog(v, 8, 3)), j
+    finally:
+        emul.emul_set_affine(0, 0)
 
 
 @pytest.mark.parametrize("table", [0, 1])
@@ -198,6 +210,14 @@ def test_msm_chunked(emul, table):
         assert emul.emul_msm_chunked(1, table, c, S, ptr(aligned(O.affines_to_bytes(cv, pts))), SZ(n),
                                      ptr(aligned(O.fes_to_bytes(sc, cv.order))), chunks, ptr(out)) == 0
         assert out.tobytes() == want, (c, S, chunks)
+    try:   # chunks + affine rounds
+        emul.emul_set_affine(3, 4)
+        out = np.zeros(96, np.uint8)
+        assert emul.emul_msm_chunked(1, table, 5, 7, ptr(aligned(O.affines_to_bytes(cv, pts))), SZ(n),
+                                     ptr(aligned(O.fes_to_bytes(sc, cv.order))), 3, ptr(out)) == 0
+        assert out.tobytes() == want
+    finally:
+        emul.emul_set_affine(0, 0)
 
 
 @pytest.mark.parametrize("fid", [O.FIELD_FQ, O.FIELD_FP])

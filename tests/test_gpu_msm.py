@@ -152,8 +152,11 @@ def test_msm_argument_errors(gpu_lib):
         G.Generators.from_affine_bytes(0, b"", table=False)
 
 
-def test_msm_batch_dev(gpu_lib):
-    """vdfgpu_msm_batch_dev: three scalar vectors of different lengths, one pass, device pointers."""
+@pytest.mark.parametrize("affine", ["0", "2"])
+def test_msm_batch_dev(gpu_lib, affine, monkeypatch):
+    """vdfgpu_msm_batch_dev: three scalar vectors of different lengths, one pass, device pointers (also with the
+    batched-affine halving rounds forced on at this small size)."""
+    monkeypatch.setenv("VDFGPU_MSM_AFFINE", affine)
     import ctypes
 
     import torch
@@ -191,6 +194,8 @@ def test_msm_host_chunked_overlap(gpu_lib, table, monkeypatch):
     for chunks in ("2", "4", "7"):
         monkeypatch.setenv("VDFGPU_MSM_CHUNKS", chunks)
         assert g.commit_bytes(sb) == single
+    monkeypatch.setenv("VDFGPU_MSM_AFFINE", "2")   # chunks + batched-affine halving rounds
+    assert g.commit_bytes(sb) == single
     assert O.jac_from_bytes(cv, single) == cv.msm_known_dlog(sc, k0, d)
 
 
