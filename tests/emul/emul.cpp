@@ -115,9 +115,10 @@ int emul_msm_batch(int curve, int table, uint32_t c, uint32_t S, const void* aff
   MsmPlan p = plan_for(n, n, table, c, S, 4, 2, 1);
   p.batch = k;
   size_t total = 0;
-  for (uint32_t j = 0; j < k; j++) total += lens[j];
+  for (uint32_t j = 0; j < k && j < MSM_MAX_BATCH; j++) total += lens[j];
   std::vector<fe> sc(total + 1);
-  std::memcpy(sc.data(), scalars, total * 32);
+  const fe* src = static_cast<const fe*>(scalars);
+  for (size_t q = 0; q < total; q++) sc[q] = src[q];
   ScalarSet ss{{nullptr, nullptr, nullptr, nullptr}};
   size_t off = 0;
   for (uint32_t j = 0; j < k; j++) { ss.v[j] = sc.data() + off; p.len[j] = lens[j]; off += lens[j]; }
