@@ -47,6 +47,26 @@ __global__ void __launch_bounds__(256) probe(uint32_t* sink, uint32_t seed, int 
         for (int k = 0; k < 4; k++)
           asm volatile("mad.lo.cc.u32 %0, %3, %4, %0; madc.hi.cc.u32 %1, %3, %4, %1; addc.u32 %2, %2, 0;"
                        : "+r"(a[2 * k]), "+r"(a[2 * k + 1]), "+r"(a[(2 * k + 3) % 8]) : "r"(y[4 * s + k]), "r"(b));
+      } else if (MODE == 7 || MODE == 8) {
+        // FP64 pipe: 4 independent fma.rz.f64 (DFMA) per set on doubles kept in the integer registers' bit patterns
+        // (the 52-bit-limb multiplier of Emmart et al. forms its products this way); MODE 8 adds 2 wide integer
+        // MACs per set to see whether the two pipes issue concurrently.
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          double acc = __hiloint2double((int)(a[2 * k + 1] & 0x000fffffu) | 0x43300000, (int)a[2 * k]);
+          double m1 = __hiloint2double(0x43300000 | (int)(y[4 * s + k] & 0xfffffu), (int)b);
+          asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(acc) : "d"(m1), "d"(1.0000001));
+          asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(acc) : "d"(m1), "d"(0.9999999));
+          a[2 * k] = (uint32_t)__double2loint(acc); a[2 * k + 1] = (uint32_t)__double2hiint(acc);
+        }
+        if (MODE == 8) {
+#pragma unroll
+          for (int k = 0; k < 2; k++) {
+            uint64_t acc = ((uint64_t)a[4 * k + 1] << 32) | a[4 * k];
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(y[4 * s + k]), "r"(b));
+            a[4 * k] = (uint32_t)acc; a[4 * k + 1] = (uint32_t)(acc >> 32);
+          }
+        }
       } else if (MODE == 6) {  // separate lo and hi MACs with carry chains (the CIOS-row formulation), 4 products
         asm volatile("mad.lo.cc.u32 %0, %8, %12, %0; madc.lo.cc.u32 %1, %9, %12, %1; madc.lo.cc.u32 %2, %10, %12, %2; madc.lo.cc.u32 %3, %11, %12, %3; addc.u32 %4, %4, 0;"
                      "mad.hi.cc.u32 %1, %8, %12, %1; madc.hi.cc.u32 %2, %9, %12, %2; madc.hi.cc.u32 %3, %10, %12, %3; madc.hi.cc.u32 %4, %11, %12, %4; addc.u32 %5, %5, 0;"
@@ -90,5 +110,7 @@ int main() {
   run<4>("2 addc chains of 8 (IADD3.X), per add", 16);
   run<5>("8 x (wide pair carry-out + addc)", 8);
   run<6>("2 x CIOS-row of 4 products (lo chain + hi chain)", 8);
+  run<7>("fma.rz.f64 x16 (DFMA), per DFMA", 16);
+  run<8>("fma.rz.f64 x16 + mad.wide.u32 x4 together, per DFMA", 16);
   return 0;
 }
