@@ -130,24 +130,44 @@ struct AffineFwdFn {
   VDF_HD void operator()(size_t t) const {
     const uint32_t M = *m_out;
     fe run = F::one();
-    for (uint32_t j = 0; j < K; j++) {
-      uint64_t o64 = (uint64_t)j * T + t;
-      if (o64 >= M) break;
-      const uint32_t o = (uint32_t)o64, r2 = rb[o];
-      if (r2 == PAIR_NONE) continue;
-      const uint32_t r1 = ra[o];
-      fe x1 = in.x(r1), x2 = in.x(r2);
-      fe d = F::sub(x2, x1);
-      if (F::is_zero(d) || F::is_zero(x1) || F::is_zero(x2)) {
-        affine_t a = in.template get<F>(r1), b = in.template get<F>(r2);
-        int kind = pair_kind<F>(a, b);
-        if (kind == PAIR_DBL) d = F::dbl(a.y);
-        else if (kind != PAIR_ADD) continue;
+    // Software pipeline: the gathers of output j+1 are issued before the multiplication of output j, so two
+    // iterations of random loads are in flight per thread (round 1 is bound by the latency of its gathers).
+    uint32_t r1 = 0, r2 = PAIR_NONE;
+    fe x1 = F::zero(), x2 = F::zero();
+    bool live = t < M;
+    if (live) load(t, r1, r2, x1, x2);
+    for (uint32_t j = 0; live; j++) {
+      const uint32_t o = (uint32_t)((uint64_t)j * T + t);
+      const uint64_t on = (uint64_t)(j + 1) * T + t;
+      const bool next = j + 1 < K && on < M;
+      uint32_t n1 = 0, n2 = PAIR_NONE;
+      fe nx1 = F::zero(), nx2 = F::zero();
+      if (next) load((uint32_t)on, n1, n2, nx1, nx2);
+      if (r2 != PAIR_NONE) {
+        fe d = F::sub(x2, x1);
+        bool use = true;
+        if (F::is_zero(d) || F::is_zero(x1) || F::is_zero(x2)) {
+          affine_t a = in.template get<F>(r1), b = in.template get<F>(r2);
+          int kind = pair_kind<F>(a, b);
+          if (kind == PAIR_DBL) d = F::dbl(a.y);
+          else if (kind != PAIR_ADD) use = false;
+        }
+        if (use) {
+          fe_store(prefix + o, run);
+          run = F::mul(run, d);
+        }
       }
-      fe_store(prefix + o, run);
-      run = F::mul(run, d);
+      r1 = n1; r2 = n2; x1 = nx1; x2 = nx2;
+      live = next;
     }
     fe_store(ptot + t, run);
+  }
+  VDF_HD void load(uint32_t o, uint32_t& r1, uint32_t& r2, fe& x1, fe& x2) const {
+    r2 = rb[o];
+    if (r2 == PAIR_NONE) return;
+    r1 = ra[o];
+    x1 = in.x(r1);
+    x2 = in.x(r2);
   }
 };
 
@@ -247,6 +267,9 @@ static inline size_t affine_round_cap(size_t e_in, size_t nbk) { return (e_in + 
 #ifndef VDF_AFF_BWD_MINB
 #define VDF_AFF_BWD_MINB 5
 #endif
+#ifndef VDF_AFF_FWD_MINB
+#define VDF_AFF_FWD_MINB 7
+#endif
 
 // Runs `rounds` halving rounds.  In: the sorted references (sref, offs) over `pts`.  Out: *list_x / *list_y /
 // *list_offs describe the reduced list (x and y arrays share ONE allocation, free *list_x and *list_offs).
@@ -274,7 +297,7 @@ void msm_affine_rounds(L& L_, uint32_t rounds, uint32_t K, uint32_t NBK, const u
     L_.exclusive_scan(cnt, offs_out, NBK);
     L_.template run<128>((cap + PairListFn::CH - 1) / PairListFn::CH,
                          PairListFn{offs_in, offs_out, NBK, r == 0 ? sref : nullptr, ra, rb});
-    L_.template run<128>(T, AffineFwdFn<F>{in, ra, rb, offs_out + NBK, T, Kr, prefix, ptot});
+    L_.template run<128, VDF_AFF_FWD_MINB>(T, AffineFwdFn<F>{in, ra, rb, offs_out + NBK, T, Kr, prefix, ptot});
     L_.template run<64>((T + BatchInvFn<F>::J - 1) / BatchInvFn<F>::J, BatchInvFn<F>{ptot, T});
     L_.template run<128, VDF_AFF_BWD_MINB>(T, AffineBwdFn<F>{in, ra, rb, offs_out + NBK, T, Kr, prefix, ptot, out,
                                                              out + cap});
