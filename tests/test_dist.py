@@ -55,7 +55,17 @@ def _worker(rank, world, port, n, q):
         total = D.sharded_commit(commit_shard, combine)
         want = O.jac_to_bytes(cv, cv.msm_known_dlog(sc, k0, d))
         gathered = D.all_gather_bytes(bytes([rank]) * 5)
-        q.put((rank, total == want, gathered == [bytes([r]) * 5 for r in range(world)]))
+        # sharded MinRoot verification: 7 chains (ragged 4 + 3), chain 5 corrupted; the oracle plays the checker
+        vdf = O.MinRootVDF(O.FIELD_FQ)
+        origs = [O.State(3 + k, 5 * k + 1, 0) for k in range(7)]
+        results = [vdf.eval(o, 6) for o in origs]
+        results[5] = O.State(results[5].x, (results[5].y + 1) % vdf.m, results[5].i)
+
+        def check_shard(lo, cnt):
+            return bytes(1 if vdf.check(results[k], 6, origs[k]) else 0 for k in range(lo, lo + cnt))
+
+        verdicts = D.sharded_verify(check_shard, 7)
+        q.put((rank, total == want, gathered == [bytes([r]) * 5 for r in range(world)] and verdicts == bytes([1, 1, 1, 1, 1, 0, 1])))
     finally:
         dist.destroy_process_group()
 

@@ -45,3 +45,24 @@ def sharded_commit(commit_shard: Callable[[], bytes], combine: Callable[[List[by
 def shard_chains(n: int, rank: int, world: int) -> Tuple[int, int]:
     """Batched MinRoot verification: chains are independent, shard by index, no collective."""
     return shard_range(n, rank, world)
+
+
+def sharded_verify(check_shard: Callable[[int, int], bytes], n: int, group=None) -> bytes:
+    """Batched MinRoot verification of n independent (result, t, original) triples over the process group:
+    check_shard(first, count) -> one verdict byte per chain of this rank's slice (on GPUs:
+    PallasVDF.check_batch on results[first:first+count]); the verdict bytes are all-gathered so that every rank
+    returns the n verdicts in chain order.  The checks themselves need no exchange."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        out = check_shard(0, n)
+        if len(out) != n:
+            raise ValueError("check_shard returned the wrong number of verdicts")
+        return out
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    first, count = shard_range(n, rank, world)
+    mine = check_shard(first, count)
+    if len(mine) != count:
+        raise ValueError("check_shard returned the wrong number of verdicts")
+    width = (n + world - 1) // world                     # slices differ by at most one chain: pad to equal length
+    parts = all_gather_bytes(mine + bytes(width - count), group)
+    return b"".join(parts[r][:shard_range(n, r, world)[1]] for r in range(world))
