@@ -614,8 +614,8 @@ void msm_accumulate(L& L_, const MsmPlan& p, const affine_t* pts, const ScalarSe
     size_t s2 = e_cap / (148 * 768);
     if (s2 < 32) s2 = 32;
     if (s2 < S) S = (uint32_t)s2;
-    S = fit_waves(e_cap, S, (size_t)148 * 5 * 128);   // the shortened list is only a wave or two of ranges
   }
+  S = fit_waves(e_cap, S, (size_t)148 * 5 * 128);   // a few waves of ranges: no partly filled last wave
 
   // accumulate over fixed-size ranges of the sorted list
   size_t T_acc = (e_cap + S - 1) / S;
