@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Multi-GPU parity on real NCCL, one process per GPU:
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 tools/dist_check.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 tests/gpu/dist_check.py
 (1) point-range-sharded MSM: every rank commits its contiguous slice of 2^18 seeded scalars over its slice of the
     generators (k0 + i d) G, the 96-byte partials are all-gathered and summed on the GPU; the result must equal
     (sum s_i (k0 + i d)) G from Python integers on every rank;
@@ -13,7 +13,7 @@ import random
 import sys
 from pathlib import Path
 
-sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 

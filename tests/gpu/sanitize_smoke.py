@@ -1,10 +1,10 @@
 #!/usr/bin/env python
 """Small end-to-end pass over every kernel family for compute-sanitizer (memcheck / racecheck):
-   compute-sanitizer --tool memcheck python tools/sanitize_smoke.py"""
+   compute-sanitizer --tool memcheck python tests/gpu/sanitize_smoke.py"""
 import sys
 from pathlib import Path
 
-sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 import __graft_entry__ as ge  # noqa: E402
 
 ge.smoke()

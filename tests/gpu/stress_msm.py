@@ -4,14 +4,14 @@ point sets (distinct points; few distinct points, i.e. buckets full of equal poi
 and scalar distributions (uniform; Nova-like: half bits, some small, some full-size; few distinct values), the
 result bytes must be identical across generator layouts (table / plain: different window size, bucket sets and
 reduction path) and across 0..5 batched-affine halving rounds.  Where the discrete logs are known the result is
-also checked against (sum s_i k_i) G computed with Python integers.  Usage: python tools/stress_msm.py [log2n ...]"""
+also checked against (sum s_i k_i) G computed with Python integers.  Usage: python tests/gpu/stress_msm.py [log2n ...]"""
 import json
 import os
 import random
 import sys
 from pathlib import Path
 
-sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
