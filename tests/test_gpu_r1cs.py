@@ -1,5 +1,7 @@
 """GPU parity for the R1CS kernels (shape source S) through the C ABI: multiply_vec,
 cross-term T, fold, and a chain of device-resident NIFS steps whose folded instance must stay satisfied."""
+import functools
+
 import pytest
 
 from oracle import pasta as O
@@ -9,14 +11,18 @@ from vdf_b200 import msm as G
 pytestmark = pytest.mark.gpu
 
 
-def _instance(fid, t, k, aug):
-    """k-th fresh instance of the step shape: result of a seed-42 chain advanced k segments."""
+@functools.lru_cache(maxsize=None)
+def _chain_state(fid, t, k):
+    """State of the seed-42 chain after k + 1 segments of t rounds (the slow fifth-root direction, oracle)."""
     ovdf = O.MinRootVDF(fid)
-    rng = O.XorShiftRng()
-    s = O.State(O.field_random(rng, ovdf.m), 0, 1)
-    for _ in range(k + 1):
-        s = ovdf.eval(s, t)
-    return O.make_step_instance(fid, t, s, aug_cons=aug)
+    if k < 0:
+        return O.State(O.field_random(O.XorShiftRng(), ovdf.m), 0, 1)
+    return ovdf.eval(_chain_state(fid, t, k - 1), t)
+
+
+def _instance(fid, t, k, aug):
+    """k-th fresh instance of the step shape: result of a seed-42 chain advanced k + 1 segments."""
+    return O.make_step_instance(fid, t, _chain_state(fid, t, k), aug_cons=aug)
 
 
 @pytest.mark.parametrize("fid", [O.FIELD_FQ, O.FIELD_FP])
@@ -90,6 +96,45 @@ def test_running_prover_chain(gpu_lib, fid, cid):
         assert prover.U.u == ur and prover.U.X == Xr
         assert prover.U.comm_W == cv.msm_known_dlog(Wr, k0, d)
         assert prover.U.comm_E == cv.msm_known_dlog(Er, k0, d)
+
+
+@pytest.mark.parametrize("fid,cid,t", [(O.FIELD_FQ, O.CURVE_PALLAS, 1024), (O.FIELD_FP, O.CURVE_VESTA, 1024),
+                                       (O.FIELD_FQ, O.CURVE_PALLAS, 4096), (O.FIELD_FQ, O.CURVE_PALLAS, 16384)])
+def test_fold_step_at_baseline_sizes(gpu_lib, fid, cid, t):
+    """BASELINE config 3 sizes (t = 1024 / 4096 / 16384 MinRoot rounds per fold step + the ~10k-constraint augmented block):
+    one NIFS fold against a RELAXED running instance (u != 1, E != 0), every output compared with the oracle --
+    multiply_vec, the cross-term T, both commitments by the known-discrete-log identity, the folded W, E, u, X,
+    and is_sat_relaxed of the result."""
+    cv = O.CURVES[cid]
+    aug = 9800
+    shape, W0, X0, _ = _instance(fid, t, 0, aug)
+    assert shape.num_cons == 3 * t + 1 + aug
+    gs = N.R1CSShape(fid, shape.num_cons, shape.num_vars, shape.num_io, shape.A, shape.B, shape.C)
+    z = shape.z_of(W0, 1, X0)
+    assert list(gs.multiply_vec(z)) == shape.multiply_vec(z)
+    k0, d = 991, 5
+    gens = G.Generators.progression(cid, k0, d, max(shape.num_cons, shape.num_vars), table=True)
+    prover = N.RunningProver(gs, gens)
+    # make the running instance properly relaxed first: fold instance 1 into instance 0 with the oracle
+    _, W1, X1, _ = _instance(fid, t, 1, aug)
+    r0 = 0x1F2E3D4C5B6A79880123456789ABCDEF
+    T0 = shape.cross_term(W0, 1, X0, W1, X1)
+    Wr, Er = O.fold_vec(W0, W1, r0, shape.m), O.fold_vec([0] * shape.num_cons, T0, r0, shape.m)
+    ur, Xr = (1 + r0) % shape.m, [(a + r0 * b) % shape.m for a, b in zip(X0, X1)]
+    assert shape.is_sat_relaxed(Wr, Er, ur, Xr)
+    U = N.RelaxedR1CSInstance(comm_W=cv.msm_known_dlog(Wr, k0, d), comm_E=cv.msm_known_dlog(Er, k0, d), X=list(Xr), u=ur)
+    prover.set_running(Wr, Er, U)
+    # the GPU fold of instance 2
+    _, W2, X2, _ = _instance(fid, t, 2, aug)
+    T_want = shape.cross_term(Wr, ur, Xr, W2, X2)
+    comm_T, r = prover.prove_step(W2, X2)
+    assert comm_T == cv.msm_known_dlog(T_want, k0, d)
+    Wn, En = O.fold_vec(Wr, W2, r, shape.m), O.fold_vec(Er, T_want, r, shape.m)
+    un, Xn = (ur + r) % shape.m, [(a + r * b) % shape.m for a, b in zip(Xr, X2)]
+    assert prover.get_running() == (Wn, En, un, Xn)
+    assert shape.is_sat_relaxed(Wn, En, un, Xn)
+    assert prover.U.comm_W == cv.msm_known_dlog(Wn, k0, d)
+    assert prover.U.comm_E == cv.msm_known_dlog(En, k0, d)
 
 
 def test_r1cs_argument_errors(gpu_lib):
