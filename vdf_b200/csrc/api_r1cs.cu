@@ -46,8 +46,11 @@ static void launch_multiply_vec(CudaLaunch& L, const vdfgpu_r1cs* s, ZView z, fe
 }
 
 static void launch_cross_term(CudaLaunch& L, const vdfgpu_r1cs* s, ZView z1, ZView z2, fe* T) {
-  if (s->field == VDFGPU_FP) L.run<128>(s->cons, CrossTermFn<Fp>{s->view(), z1, z2, T});
-  else L.run<128>(s->cons, CrossTermFn<Fq>{s->view(), z1, z2, T});
+#ifndef VDF_CT_MINB
+#define VDF_CT_MINB 8
+#endif
+  if (s->field == VDFGPU_FP) L.run<128, VDF_CT_MINB>(s->cons, CrossTermFn<Fp>{s->view(), z1, z2, T});
+  else L.run<128, VDF_CT_MINB>(s->cons, CrossTermFn<Fq>{s->view(), z1, z2, T});
 }
 
 static void launch_fold(CudaLaunch& L, int field, fe* W1, const fe* W2, size_t nW, fe* E1, const fe* T, size_t nE,

@@ -80,25 +80,27 @@ struct CrossTermFn {
   fe* T;
   VDF_HD void operator()(size_t idx) const {
     uint32_t row = (uint32_t)idx;
-    fe d1[3], d2[3];
     const fe one = F::one(), minus_one = F::neg(F::one());
+    // the A and B products are combined as soon as both are known, so at most four dot products are live at once
+    fe a1, a2, t;
     for (uint32_t mat = 0; mat < 3; mat++) {
-      fe a1 = F::zero(), a2 = F::zero();
+      fe s1 = F::zero(), s2 = F::zero();
       uint32_t r = mat * m.cons + row;
       uint32_t lo = m.row_ptr[r], hi = m.row_ptr[r + 1];
       for (uint32_t k = lo; k < hi; k++) {
         fe v = fe_load(m.val + k);
         uint32_t c = m.col[k];
-        a1 = mul_acc<F>(a1, v, z_at<F>(z1, m.vars, c), one, minus_one);
-        a2 = mul_acc<F>(a2, v, z_at<F>(z2, m.vars, c), one, minus_one);
+        s1 = mul_acc<F>(s1, v, z_at<F>(z1, m.vars, c), one, minus_one);
+        s2 = mul_acc<F>(s2, v, z_at<F>(z2, m.vars, c), one, minus_one);
       }
-      d1[mat] = a1;
-      d2[mat] = a2;
+      if (mat == 0) {
+        a1 = s1; a2 = s2;
+      } else if (mat == 1) {
+        t = F::add(F::mul(a1, s2), F::mul(a2, s1));          // Az1*Bz2 + Az2*Bz1
+      } else {
+        t = F::sub(F::sub(t, F::mul(fe_load(z1.u), s2)), s1);   // - u1*Cz2 - Cz1
+      }
     }
-    fe u1 = fe_load(z1.u);
-    fe t = F::add(F::mul(d1[0], d2[1]), F::mul(d2[0], d1[1]));
-    t = F::sub(t, F::mul(u1, d2[2]));
-    t = F::sub(t, d1[2]);
     fe_store(T + row, t);
   }
 };
