@@ -30,7 +30,7 @@ struct ZView {   // z = [W | u | X]
 template <class F>
 VDF_HD fe z_at(const ZView& z, uint32_t vars, uint32_t col) {
   const fe* p = col < vars ? z.W + col : (col == vars ? z.u : z.X + (col - vars - 1));
-  return fe_load(p);
+  return fe_load_gather(p);   // random 32-byte gather: do not pull the rest of the line
 }
 
 // acc += v * x.  Most R1CS coefficients are +1 or -1 (every A/B entry and all but one C entry of the MinRoot
