@@ -35,7 +35,7 @@ void field_op(int op, const fe* a, const fe* b, fe* out, size_t n) {
   }
 }
 
-uint32_t g_affine_rounds = 0, g_affine_K = 8;   // set by emul_set_affine
+uint32_t g_affine_rounds = 0, g_affine_K = 8, g_rec_warp = 0;   // set by emul_set_affine
 
 MsmPlan plan_for(size_t n, size_t stride, int table, uint32_t c, uint32_t S, uint32_t G, uint32_t logm, int is_mont) {
   MsmPlan p;
@@ -55,12 +55,19 @@ MsmPlan plan_for(size_t n, size_t stride, int table, uint32_t c, uint32_t S, uin
   p.raw_jacobian = 0;
   p.affine_rounds = g_affine_rounds;
   p.affine_K = g_affine_K;
+  p.rec_warp = g_rec_warp;
   return p;
 }
 
 }  // namespace
 
 extern "C" {
+
+// record levels in groups of 32 (the serial mirror of RecWarpLevelFn) for every following emul_msm* call
+int emul_set_recwarp(uint32_t on) {
+  g_rec_warp = on;
+  return 0;
+}
 
 // batched-affine halving rounds (msm_affine.cuh) for every following emul_msm* call; 0 = off
 int emul_set_affine(uint32_t rounds, uint32_t K) {

@@ -86,6 +86,13 @@ def test_msm_skewed_and_edges(emul):
     for table in (0, 1):
         for c, S, G in ((6, 4, 4), (9, 8, 5)):   # tiny S: > 4096 records -> record levels run
             assert _msm(emul, 0, table, c, S, G, 2, pts, sc) == want
+    try:   # record levels in groups of 32 records (host mirror of the warp-cooperative level)
+        emul.emul_set_recwarp(1)
+        for table in (0, 1):
+            for c, S in ((6, 4), (9, 2), (4, 3)):
+                assert _msm(emul, 0, table, c, S, 4, 2, pts, sc) == want
+    finally:
+        emul.emul_set_recwarp(0)
     assert _msm(emul, 0, 0, 8, 16, 4, 3, [], []) == bytes(96)
     assert _msm(emul, 0, 0, 8, 16, 4, 3, pts[:1], [0]) == bytes(96)
     assert _msm(emul, 0, 1, 8, 16, 4, 3, pts[:1], [5]) == O.jac_to_bytes(cv, cv.mul(5, pts[0]))

@@ -82,6 +82,8 @@ static MsmPlan make_plan(const vdfgpu_gens* g, size_t n, bool is_mont, uint32_t 
   p.logm = 3;
   if (const char* s = std::getenv("VDFGPU_MSM_G")) p.G = (uint32_t)std::atoi(s);
   if (const char* s = std::getenv("VDFGPU_MSM_LOGM")) p.logm = (uint32_t)std::atoi(s);
+  p.rec_warp = 1;
+  if (const char* s = std::getenv("VDFGPU_MSM_RECWARP")) p.rec_warp = (uint32_t)std::atoi(s);
   // batched-affine halving rounds (msm_affine.cuh): worth their fixed costs only in the throughput regime and
   // while the buckets still hold >= 16 entries on average
   p.affine_rounds = 0;

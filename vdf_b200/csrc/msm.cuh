@@ -49,6 +49,7 @@ struct MsmPlan {
   uint32_t batch = 1;      // independent scalar vectors over the SAME points (one result each), <= MSM_MAX_BATCH
   uint32_t len[4] = {0, 0, 0, 0};  // length of each vector (<= n); shorter vectors are zero-padded
   uint32_t raw_jacobian = 0;       // 1: write (X*ZZ, Y*ZZZ, ZZ) without the final inversion (caller normalises)
+  uint32_t rec_warp = 0;           // 1: record levels by warp-cooperative segmented sums (RecWarpLevelFn)
   uint32_t affine_rounds = 0;      // batched-affine halving rounds before the XYZZ accumulation (msm_affine.cuh)
   uint32_t affine_K = 64;          // additions per thread and round sharing one running product
 };
@@ -316,6 +317,76 @@ struct RecLevelFn {
       flags |= in_hdr[r].flags;
       C::add(acc, in_pt[r]);
     }
+  }
+};
+
+// The same level with one WARP per 32 records: a segmented sum over the lanes by shuffles (5 steps, one point addition
+// each) instead of a serial loop in one thread -- 32 records -> <= 2 with a chain of 5 additions, where RecLevelFn
+// needs 8 additions to bring 8 down to 2.  Launched with a multiple of 32 threads; index = input record slot.
+// (The CPU emulation runs the serial functor with G = 32: same outputs.)
+template <class C>
+struct RecWarpLevelFn {
+  const RecHdr* in_hdr;
+  const xyzz_t* in_pt;
+  size_t n_in;
+  xyzz_t* buckets;
+  RecHdr* out_hdr;  // [2 * groups of 32]
+  xyzz_t* out_pt;
+  VDF_HD void operator()(size_t idx) const {
+#if defined(__CUDA_ARCH__)
+    const unsigned lane = threadIdx.x & 31u, full = 0xffffffffu;
+    const size_t g = idx >> 5;
+    if (lane == 0) {
+      out_hdr[2 * g].bucket = REC_NONE;
+      out_hdr[2 * g + 1].bucket = REC_NONE;
+    }
+    __syncwarp();
+    uint32_t own = idx < n_in ? in_hdr[idx].bucket : REC_NONE;
+    uint32_t flags = own != REC_NONE ? in_hdr[idx].flags : 0u;
+    xyzz_t v = C::identity();
+    if (own != REC_NONE) v = in_pt[idx];
+    // empty slots join the run on their left (identity value), so that runs are contiguous in the warp
+    uint32_t key = own;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t up = __shfl_up_sync(full, key, d);
+      if (lane >= (unsigned)d && key == REC_NONE) key = up;
+    }
+    const uint32_t left = __shfl_up_sync(full, key, 1);
+    const bool head = key != REC_NONE && (lane == 0 || left != key);
+    // is there a real run before this lane's run?  (the first unfinished run goes to slot 2g, a later one to 2g+1)
+    const unsigned heads = __ballot_sync(full, head);
+    const bool first_run = (heads & ((1u << lane) - 1u)) == 0u;
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t ok = __shfl_down_sync(full, key, d);
+      const uint32_t of = __shfl_down_sync(full, flags, d);
+      xyzz_t o;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        o.X.v[k] = __shfl_down_sync(full, v.X.v[k], d);
+        o.Y.v[k] = __shfl_down_sync(full, v.Y.v[k], d);
+        o.ZZ.v[k] = __shfl_down_sync(full, v.ZZ.v[k], d);
+        o.ZZZ.v[k] = __shfl_down_sync(full, v.ZZZ.v[k], d);
+      }
+      if (lane + d < 32 && ok == key && key != REC_NONE) {
+        C::add(v, o);
+        flags |= of;
+      }
+    }
+    if (head) {
+      if ((flags & REC_FIRST) && (flags & REC_LAST)) {
+        buckets[key] = v;
+      } else {
+        const size_t slot = first_run ? 2 * g : 2 * g + 1;
+        out_hdr[slot].bucket = key;
+        out_hdr[slot].flags = flags;
+        out_pt[slot] = v;
+      }
+    }
+#else
+    if ((idx & 31) == 0) RecLevelFn<C>{in_hdr, in_pt, n_in, buckets, out_hdr, out_pt, 32u}(idx >> 5);
+#endif
   }
 };
 
@@ -637,6 +708,27 @@ void msm_accumulate(L& L_, const MsmPlan& p, const affine_t* pts, const ScalarSe
   // stop at 4096 records.  Small problems are latency-bound (every level is a serial chain of <= G point
   // additions, and the owner pass is serial in the number of pieces of the heaviest bucket): G = 8, run
   // the levels down to 256 records.
+  if (p.rec_warp) {
+    // one warp per 32 records (RecWarpLevelFn): 16x fewer records per level with a chain of 5 additions; down to 64
+    // records so that the serial owner pass stays short even when one bucket owns every remaining piece
+    // The warp level spends 5 lane-additions per record where the serial one spends 1: with many records in long
+    // runs (several pieces per bucket) the first levels are throughput-bound, so they stay serial (G = 8).
+    const bool long_runs = n_rec > 2 * (size_t)NBK;
+    while (n_rec > 64) {
+      const bool serial = long_runs && n_rec > 65536;
+      const size_t per = serial ? 8 : 32;
+      size_t groups = (n_rec + per - 1) / per;
+      if (!hdr_b) {
+        hdr_b = L_.template alloc<RecHdr>(2 * groups);
+        pt_b = L_.template alloc<xyzz_t>(2 * groups);
+      }
+      if (serial) L_.template run<128>(groups, RecLevelFn<C>{hdr_a, pt_a, n_rec, buckets, hdr_b, pt_b, 8u});
+      else L_.template run<128>(groups * 32, RecWarpLevelFn<C>{hdr_a, pt_a, n_rec, buckets, hdr_b, pt_b});
+      RecHdr* th = hdr_a; hdr_a = hdr_b; hdr_b = th;
+      xyzz_t* tp = pt_a; pt_a = pt_b; pt_b = tp;
+      n_rec = 2 * groups;
+    }
+  } else {
   const bool small = n_rec <= (1u << 17);
   const uint32_t G = small ? 8u : (p.G < 4 ? 4u : p.G);
   const size_t rec_stop = small ? 256 : 4096;
@@ -650,6 +742,7 @@ void msm_accumulate(L& L_, const MsmPlan& p, const affine_t* pts, const ScalarSe
     RecHdr* th = hdr_a; hdr_a = hdr_b; hdr_b = th;
     xyzz_t* tp = pt_a; pt_a = pt_b; pt_b = tp;
     n_rec = 2 * groups;
+  }
   }
   L_.template run<128>(n_rec, RecOwnerFn<C>{hdr_a, pt_a, n_rec, buckets});
 
