@@ -502,6 +502,74 @@ struct SumFn {
   }
 };
 
+// Latency version of SumFn: one WARP per 32 consecutive elements of a row, summed by a shuffle tree (5 steps of one
+// addition) -- 32x fewer elements per level where the radix-4 SumFn gives 4x for 3 additions.  It spends 5
+// lane-additions per element, so it is used only when the level is small (msm_tree_levels).  Index = row * Tw * 32
+// + warp * 32 + lane with Tw = ceil(cnt / 32); launched with whole warps.
+template <class C>
+struct SumWarpFn {
+  const xyzz_t* in;
+  size_t in_stride;
+  uint32_t cnt, Tw;
+  xyzz_t* out;
+  size_t out_stride;
+  VDF_HD void operator()(size_t idx) const {
+    const size_t w = idx >> 5;
+    const uint32_t row = (uint32_t)(w / Tw), t = (uint32_t)(w - (size_t)row * Tw);
+    const xyzz_t* src = in + (size_t)row * in_stride;
+#if defined(__CUDA_ARCH__)
+    const unsigned lane = threadIdx.x & 31u, full = 0xffffffffu;
+    const uint32_t j = t * 32u + lane;
+    xyzz_t v = C::identity();
+    if (j < cnt) v = src[j];
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+      xyzz_t o;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        o.X.v[k] = __shfl_down_sync(full, v.X.v[k], d);
+        o.Y.v[k] = __shfl_down_sync(full, v.Y.v[k], d);
+        o.ZZ.v[k] = __shfl_down_sync(full, v.ZZ.v[k], d);
+        o.ZZZ.v[k] = __shfl_down_sync(full, v.ZZZ.v[k], d);
+      }
+      if (lane < (unsigned)d) C::add(v, o);
+    }
+    if (lane == 0) out[(size_t)row * out_stride + t] = v;
+#else
+    if (idx & 31) return;
+    xyzz_t acc = C::identity();
+    const uint32_t lo = t * 32u, hi = lo + 32u < cnt ? lo + 32u : cnt;
+    for (uint32_t j = lo; j < hi; j++) C::add(acc, src[j]);
+    out[(size_t)row * out_stride + t] = acc;
+#endif
+  }
+};
+
+// rows x cnt  ->  rows x 1 by tree levels, ping-ponging between the two buffers (each at least rows * ceil(cnt / 4)
+// elements after the first level); returns where the result lives and its row stride
+template <class L, class C>
+const xyzz_t* msm_tree_levels(L& L_, uint32_t rows, const xyzz_t* cur, size_t& cur_stride, uint32_t cnt, xyzz_t* buf_a,
+                              xyzz_t* buf_b) {
+  xyzz_t* dst = (cur == buf_a) ? buf_b : buf_a;
+  while (cnt > 1) {
+    // small levels are pure latency: the warp tree; big ones are throughput: radix 4 per thread
+    const bool warp = cnt > 4 && (size_t)rows * cnt <= 32768;
+    uint32_t T;
+    if (warp) {
+      T = (cnt + 31) / 32;
+      L_.template run<128>((size_t)rows * T * 32, SumWarpFn<C>{cur, cur_stride, cnt, T, dst, T});
+    } else {
+      T = (cnt + 3) / 4;
+      L_.template run<128>((size_t)rows * T, SumFn<C>{cur, cur_stride, cnt, T, 4u, dst, T});
+    }
+    cur = dst;
+    cur_stride = T;
+    cnt = T;
+    dst = (dst == buf_a) ? buf_b : buf_a;
+  }
+  return cur;
+}
+
 // ---- stage 7: final (one thread) -----------------------------------------------------------------------
 template <class C>
 struct FinalFn {
@@ -559,17 +627,8 @@ void msm_bit_weighted_sum(L& L_, uint32_t NBT, const xyzz_t* arr, uint32_t B, xy
   xyzz_t* bs_a = L_.template alloc<xyzz_t>((size_t)rows * cnt);
   xyzz_t* bs_b = L_.template alloc<xyzz_t>((size_t)rows * ((cnt + 3) / 4));
   L_.template run<128>((size_t)rows * cnt, BitPairFn<C>{arr, B, nbits, bs_a});
-  const xyzz_t* cur = bs_a;
   size_t cur_stride = cnt;
-  xyzz_t* dst = bs_b;
-  while (cnt > 1) {
-    uint32_t T = (cnt + 3) / 4;
-    L_.template run<128>((size_t)rows * T, SumFn<C>{cur, cur_stride, cnt, T, 4u, dst, T});
-    cur = dst;
-    cur_stride = T;
-    cnt = T;
-    dst = (dst == bs_a) ? bs_b : bs_a;
-  }
+  const xyzz_t* cur = msm_tree_levels<L, C>(L_, rows, bs_a, cur_stride, cnt, bs_a, bs_b);
   msm_bit_combine<L, C>(L_, NBT, cur, cur_stride, arr, B, nbits, per_set);
   L_.free(bs_a); L_.free(bs_b);
 }
@@ -785,18 +844,8 @@ void msm_finish(L& L_, const MsmPlan& p, const xyzz_t* buckets, jac_t* out) {
     L_.zero(S_arr, (size_t)NBT * T0 * sizeof(xyzz_t));   // element T0-1 (weight T0) stays the identity
     L_.template run<128>((size_t)NBT * T0, ReduceLevelFn<C>{buckets, p.B, p.B, T0, p.logm, S_arr, A_arr, T0, 0, 0u});
     L_.template run<128>((size_t)bit_rows * q4, BitPairFn<C>{S_arr, T0, nbits, ra});
-    const xyzz_t* cur = ra;
     size_t cur_stride = q4;
-    uint32_t cnt = q4;
-    xyzz_t* dst = rb;
-    while (cnt > 1) {
-      uint32_t T = (cnt + 3) / 4;
-      L_.template run<128>((size_t)rows * T, SumFn<C>{cur, cur_stride, cnt, T, 4u, dst, T});
-      cur = dst;
-      cur_stride = T;
-      cnt = T;
-      dst = (dst == ra) ? rb : ra;
-    }
+    const xyzz_t* cur = msm_tree_levels<L, C>(L_, rows, ra, cur_stride, q4, ra, rb);
     xyzz_t* wsum = L_.template alloc<xyzz_t>(NBT);
     xyzz_t* per_set = L_.template alloc<xyzz_t>(NBT);
     msm_bit_combine<L, C>(L_, NBT, cur, cur_stride, S_arr, T0, nbits, wsum);
