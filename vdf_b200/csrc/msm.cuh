@@ -598,21 +598,26 @@ void msm_bit_combine(L& L_, uint32_t NBT, const xyzz_t* bitsum, size_t stride, c
   xyzz_t* terms = L_.template alloc<xyzz_t>((size_t)NBT * per);
   xyzz_t* t1 = L_.template alloc<xyzz_t>((size_t)NBT * ((per + 3) / 4));
   L_.template run<32>((size_t)NBT * per, BitScaleFn<C>{bitsum, stride, arr, B, nbits, terms});
-  const xyzz_t* cur = terms;
-  size_t cur_stride = per;
-  uint32_t cnt = per;
-  xyzz_t* dst = t1;
-  xyzz_t* spare = terms;
-  while (cnt > 4) {
-    uint32_t T = (cnt + 3) / 4;
-    L_.template run<32>((size_t)NBT * T, SumFn<C>{cur, cur_stride, cnt, T, 4u, dst, T});
-    cur = dst;
-    cur_stride = T;
-    cnt = T;
-    xyzz_t* nx = (dst == t1) ? spare : t1;
-    dst = nx;
+  if (per > 4 && per <= 32) {
+    // one warp per set sums its <= 32 terms in 5 shuffle steps
+    L_.template run<32>((size_t)NBT * 32, SumWarpFn<C>{terms, per, per, 1u, out, 1});
+  } else {
+    const xyzz_t* cur = terms;
+    size_t cur_stride = per;
+    uint32_t cnt = per;
+    xyzz_t* dst = t1;
+    xyzz_t* spare = terms;
+    while (cnt > 4) {
+      uint32_t T = (cnt + 3) / 4;
+      L_.template run<32>((size_t)NBT * T, SumFn<C>{cur, cur_stride, cnt, T, 4u, dst, T});
+      cur = dst;
+      cur_stride = T;
+      cnt = T;
+      xyzz_t* nx = (dst == t1) ? spare : t1;
+      dst = nx;
+    }
+    L_.template run<32>(NBT, SumFn<C>{cur, cur_stride, cnt, 1u, cnt, out, 1});
   }
-  L_.template run<32>(NBT, SumFn<C>{cur, cur_stride, cnt, 1u, cnt, out, 1});
   L_.free(terms); L_.free(t1);
 }
 
