@@ -10,11 +10,11 @@
 //   2 scan       exclusive prefix sum of the histogram -> bucket offsets.
 //   3 scatter    one-pass radix (counting) sort of point references by bucket id.  Order inside a bucket
 //                is arbitrary: the group is commutative and the result is canonicalised at the end.
-//   4 accumulate fixed-size ranges of the sorted list per thread (perfect balance whatever the digit
+//   4 accumulate optional batched-affine halving rounds (msm_affine.cuh), then fixed-size ranges of the sorted list per thread (perfect balance whatever the digit
 //                distribution), XYZZ mixed additions; bucket pieces that straddle a range boundary go
 //                to a record list, complete buckets are stored directly.
-//   5 fixup      segmented reduction of the record list (again range-based, log depth), then owners
-//                fold what is left.
+//   5 fixup      segmented reduction of the record list (log depth: one warp per 32 records, shuffle sums),
+//                then owners fold what is left.
 //   6 reduce     sum_j j*B_j.  Small sets: bit decomposition (row b = sum of the buckets whose index has bit
 //                b set, radix-4 tree sums, then 2^b applied per row in parallel).  Large sets: one level of
 //                chunk-local running sums, then the same bit decomposition over the chunk totals.
