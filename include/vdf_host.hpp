@@ -14,6 +14,7 @@
 #include <array>
 #include <cstdint>
 #include <cstring>
+#include <initializer_list>
 #include <optional>
 #include <stdexcept>
 #include <string>
@@ -138,6 +139,9 @@ class R1CSShape {
   R1CSShape(int field, size_t num_cons, size_t num_vars, size_t num_io, const CooMatrix& A, const CooMatrix& B,
             const CooMatrix& C)
       : field_(field), cons_(num_cons), vars_(num_vars), io_(num_io) {
+    for (const CooMatrix* m : {&A, &B, &C})
+      if (m->rows.size() != m->vals.size() || m->cols.size() != m->vals.size())
+        throw std::invalid_argument("R1CSShape: COO arrays of different lengths");
     ok_or_throw(vdfgpu_r1cs_create(field, num_cons, num_vars, num_io, A.rows.data(), A.cols.data(), A.vals.data(), A.vals.size(),
                              B.rows.data(), B.cols.data(), B.vals.data(), B.vals.size(), C.rows.data(), C.cols.data(),
                              C.vals.data(), C.vals.size(), &h_),
@@ -164,6 +168,10 @@ class R1CSShape {
   std::pair<std::vector<Fe>, Point> commit_T(const Generators& gens, const std::vector<Fe>& W1, const Fe& u1,
                                              const std::vector<Fe>& X1, const std::vector<Fe>& W2,
                                              const std::vector<Fe>& X2) const {
+    // nova-snark returns NovaError::InvalidWitnessLength here; the C ABI takes no lengths, so check before it reads
+    if (W1.size() != vars_ || W2.size() != vars_ || X1.size() != io_ || X2.size() != io_)
+      throw std::invalid_argument("commit_T: InvalidWitnessLength");
+    if (gens.len() < cons_) throw std::invalid_argument("commit_T: fewer generators than constraints");
     std::vector<Fe> T(cons_);
     Point comm{};
     ok_or_throw(vdfgpu_commit_T(h_, gens.handle(), W1.data(), u1.data(), X1.data(), W2.data(), X2.data(), T.data(), comm.data()),
@@ -187,16 +195,21 @@ inline void fold(int field, std::vector<Fe>& W1, const std::vector<Fe>& W2, std:
 // Device-resident running witness: the witness side of NIFS::prove, one call pair per fold step
 class RunningWitness {
  public:
-  RunningWitness(const R1CSShape& s, const Generators& g) { ok_or_throw(vdfgpu_running_create(s.handle(), g.handle(), &h_), "vdfgpu_running_create"); }
+  // The shape and the generators must outlive this object (the library refuses to destroy them while it exists).
+  RunningWitness(const R1CSShape& s, const Generators& g) : cons_(s.num_cons()), vars_(s.num_vars()), io_(s.num_io()) {
+    ok_or_throw(vdfgpu_running_create(s.handle(), g.handle(), &h_), "vdfgpu_running_create");
+  }
   RunningWitness(const RunningWitness&) = delete;
   RunningWitness& operator=(const RunningWitness&) = delete;
   ~RunningWitness() { if (h_) vdfgpu_running_destroy(h_); }
   void set(const std::vector<Fe>& W, const std::vector<Fe>& E, const Fe& u, const std::vector<Fe>& X) {
+    if (W.size() != vars_ || E.size() != cons_ || X.size() != io_) throw std::invalid_argument("set: InvalidWitnessLength");
     ok_or_throw(vdfgpu_running_set(h_, W.data(), E.data(), u.data(), X.data()), "vdfgpu_running_set");
   }
   struct Commitments { Point comm_W2, comm_T; };
   // commit(W2), T, commit(T): returns what the random oracle absorbs
   Commitments commit(const std::vector<Fe>& W2, const std::vector<Fe>& X2) {
+    if (W2.size() != vars_ || X2.size() != io_) throw std::invalid_argument("commit: InvalidWitnessLength");
     Commitments c{};
     ok_or_throw(vdfgpu_running_commit(h_, W2.data(), X2.data(), c.comm_W2.data(), c.comm_T.data()), "vdfgpu_running_commit");
     return c;
@@ -204,10 +217,14 @@ class RunningWitness {
   // W += r W2, E += r T, u += r, X += r X2
   void fold(const Fe& r) { ok_or_throw(vdfgpu_running_finish(h_, r.data()), "vdfgpu_running_finish"); }
   void get(std::vector<Fe>& W, std::vector<Fe>& E, Fe& u, std::vector<Fe>& X) const {
+    W.resize(vars_);
+    E.resize(cons_);
+    X.resize(io_);
     ok_or_throw(vdfgpu_running_get(h_, W.data(), E.data(), u.data(), X.data()), "vdfgpu_running_get");
   }
 
  private:
+  size_t cons_, vars_, io_;
   vdfgpu_running* h_ = nullptr;
 };
 

@@ -21,9 +21,24 @@
  *
  * Memory: "host" pointers are ordinary host memory owned by the caller for the duration of the call
  * (pinned memory makes the copies faster); "_dev" entry points take device pointers and enqueue on the
- * library stream (vdfgpu_set_stream) without synchronising.  Handles are owned by the library and freed
- * by the matching *_destroy.  Calls on one thread are ordered; the library keeps no pointer after return
+ * calling thread's stream (vdfgpu_set_stream) without synchronising.  Handles are owned by the library and
+ * freed by the matching *_destroy.  Calls on one thread are ordered; the library keeps no pointer after return
  * (except vdfgpu_msm_submit, whose buffers it owns until vdfgpu_msm_wait of that slot).
+ *
+ * Threads and devices: ONE GPU per process (vdfgpu_init(device); a call before vdfgpu_init binds device 0, which
+ * is what the literal pasta-msm entry points need).  Every entry point may be called from any thread: the library
+ * takes an internal lock only while it ENQUEUES work and waits for the GPU after releasing it, so calls from
+ * several threads overlap on the device; the stream is a per-THREAD setting; the caller's current CUDA device is
+ * restored before a call returns.  A handle must not be destroyed while another thread uses it; a generator set or
+ * shape held by a running instance cannot be destroyed (VDFGPU_ERR_STATE) until that instance is.
+ *
+ * Inputs: every 32-byte field element must be the canonical Montgomery image of a value < m, as pasta_curves'
+ * from_repr guarantees on the Rust side.  The MinRoot verdict entry points check this themselves (a non-canonical
+ * State gives ok = 0); the other entry points do not.
+ *
+ * Limits: point references are 31 bits, so windows * points of one generator set must stay below 2^31 (a table
+ * set of 2^26 points x 13 levels uses 41 %); shard larger sets by point range (vdfgpu_msm_range_dev / one set per
+ * GPU) and add the partial results with vdfgpu_point_sum.
  */
 #ifndef VDFGPU_H
 #define VDFGPU_H
@@ -61,8 +76,10 @@ int vdfgpu_shutdown(void);
 int vdfgpu_device_count(void);
 const char* vdfgpu_last_error(void);
 const char* vdfgpu_version(void);
-int vdfgpu_set_stream(void* cuda_stream); /* cudaStream_t for all subsequent work; NULL = library stream */
-int vdfgpu_synchronize(void);
+int vdfgpu_set_stream(void* cuda_stream); /* cudaStream_t for the CALLING THREAD's subsequent work; NULL = library stream */
+int vdfgpu_synchronize(void);             /* waits for the calling thread's stream */
+/* frees the preallocated MSM workspaces (one per stream that ran an MSM) and the cached pool memory */
+int vdfgpu_trim(void);
 uint64_t vdfgpu_launch_count(void);       /* kernels launched by this library so far */
 
 /* ---- a4: MSM.  Replaces pasta-msm's extern "C" mult_pippenger_{pallas,vesta}, the backend of nova's
@@ -72,6 +89,13 @@ void mult_pippenger_pallas(void* out_point96, const void* points_affine72, size_
                            const void* scalars32, bool is_mont);
 void mult_pippenger_vesta(void* out_point96, const void* points_affine72, size_t npoints,
                           const void* scalars32, bool is_mont);
+
+/* The literal entry points keep the generator sets they have seen resident (nova passes the same Vec every time):
+ * see "drop-in cache" in vdf_b200/csrc/api_core.cu.  Environment: VDFGPU_DROPIN_CACHE=0 (off),
+ * VDFGPU_DROPIN_VERIFY=sample|full|off (how a cached set is re-validated against the caller's memory; default
+ * sample), VDFGPU_DROPIN_ENTRIES (LRU size, default 4). */
+int vdfgpu_dropin_cache_clear(void);
+int vdfgpu_dropin_cache_stats(uint64_t* hits, uint64_t* misses, uint64_t* entries);
 
 /* Generators are fixed for the life of PublicParams (src/nova/proof.rs:232-237): upload/repack once. */
 int vdfgpu_gens_create(int curve, const void* points_affine72_host, size_t n, uint32_t flags,
@@ -91,9 +115,10 @@ int vdfgpu_gens_destroy(vdfgpu_gens* g);
 int vdfgpu_msm(vdfgpu_gens* g, const void* scalars32_host, size_t n, void* out_point96_host);
 int vdfgpu_msm_dev(vdfgpu_gens* g, const void* scalars32_dev, size_t n, void* out_point96_dev);
 /* Asynchronous form of vdfgpu_msm for callers with several independent commitments: submit returns once the
- * work is enqueued (use pinned host memory), wait blocks until out_point96_host of that slot is written.  The
- * upload of slot k+1 overlaps the kernels of slot k.  slot in [0, 4); a busy slot must be waited before reuse;
- * host buffers of a slot stay owned by the library until its wait returns. */
+ * work is enqueued (use pinned host memory), wait blocks until out_point96_host of that slot is written.  Every
+ * slot has its own stream: the upload AND the latency-bound stages of slot k+1 overlap the kernels of slot k.
+ * slot in [0, 4); a busy slot must be waited before reuse; host buffers of a slot stay owned by the library until
+ * its wait returns. */
 int vdfgpu_msm_submit(vdfgpu_gens* g, const void* scalars32_host, size_t n, void* out_point96_host, int slot);
 int vdfgpu_msm_wait(int slot);
 /* k <= 4 scalar vectors (lengths lens[j]) over the same generators in ONE pass: k commitments for the latency
@@ -148,6 +173,22 @@ int vdfgpu_running_commit(vdfgpu_running* f, const void* W2_host, const void* X2
                        void* comm_W2_point96_host, void* comm_T_point96_host);
 /* W <- W + r*W2, E <- E + r*T, u <- u + r, X <- X + r*X2 */
 int vdfgpu_running_finish(vdfgpu_running* f, const void* r32_host);
+
+/* SURVEY 8f rank 1 -- the step-circuit part of the fresh witness never crosses PCIe.  A bank holds, for all n steps
+ * of one proof, the 4t+1 values InverseMinRootCircuit::synthesize allocates (src/nova/proof.rs:107-126, :162-189),
+ * generated on the device from the steps' input states (x, y, i) -- the circuits of a proof are independent once the
+ * VDF states are known (src/nova/proof.rs:284-296).  Creation is asynchronous (own stream).
+ * vdfgpu_running_commit_step is vdfgpu_running_commit with
+ *   W2 = [ W2_host[0, step_offset) | bank[step] | W2_host[step_offset + 4t + 1, vars) ]
+ * W2_host has the full length; its step range is neither read nor transferred. */
+typedef struct vdfgpu_witness_bank vdfgpu_witness_bank;
+int vdfgpu_witness_bank_create(int field, const void* z_in_state96_host, uint64_t t, size_t n,
+                               vdfgpu_witness_bank** out);
+int vdfgpu_witness_bank_destroy(vdfgpu_witness_bank* b);
+int vdfgpu_witness_bank_read(const vdfgpu_witness_bank* b, size_t first_step, size_t count, void* out_fe32_host);
+int vdfgpu_running_commit_step(vdfgpu_running* f, const vdfgpu_witness_bank* bank, size_t step, size_t step_offset,
+                               const void* W2_host, const void* X2_host, void* comm_W2_point96_host,
+                               void* comm_T_point96_host);
 
 /* ---- a8: batched MinRoot verification.  Replaces a loop of MinRootVDF::check (src/minroot.rs:369-371)
  * / Evaluation::verify (:424-426) over independent chains.  ok_out[k] = 1 iff

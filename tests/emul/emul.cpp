@@ -37,6 +37,43 @@ void field_op(int op, const fe* a, const fe* b, fe* out, size_t n) {
 
 uint32_t g_affine_rounds = 0, g_affine_K = 8, g_rec_warp = 0;   // set by emul_set_affine
 
+// HostLaunch whose temporaries come from ONE block sized beforehand by the sizing pass (PlanLaunch), exactly as the
+// product's CudaLaunch does with its per-stream arena: a disagreement between the sizing pass and the run throws.
+struct HostArenaLaunch : HostLaunch {
+  Arena arena;
+  std::vector<uint8_t> block;
+  explicit HostArenaLaunch(size_t bytes) : block(bytes + 64) {
+    arena.base = block.data() + (64 - reinterpret_cast<uintptr_t>(block.data()) % 64) % 64;
+    arena.reset(bytes);
+  }
+  template <class T>
+  T* alloc(size_t count) { return reinterpret_cast<T*>(arena.alloc(count * sizeof(T))); }
+  void free(void* p) { arena.free(p); }
+  void exclusive_scan(const uint32_t* in, uint32_t* out, size_t n) {
+    size_t tiles = (n + 2047) / 2048;
+    if (tiles == 0) tiles = 1;
+    uint32_t* t = alloc<uint32_t>(tiles);   // mirrors CudaLaunch::exclusive_scan's temporary
+    HostLaunch::exclusive_scan(in, out, n);
+    free(t);
+  }
+};
+
+// whole MSM through the arena: returns 0, or -7 when the sizing pass and the run disagree
+template <class C, class SF>
+int run_msm_arena(const MsmPlan& p, const affine_t* pts, const ScalarSet& ss, jac_t* out) {
+  PlanLaunch PL;
+  ScalarSet none{{nullptr, nullptr, nullptr, nullptr}};
+  msm_run<PlanLaunch, C, SF>(PL, p, nullptr, none, nullptr);
+  HostArenaLaunch L(PL.arena.high);
+  try {
+    msm_run<HostArenaLaunch, C, SF>(L, p, pts, ss, out);
+  } catch (const std::exception&) {
+    return -7;
+  }
+  if (L.arena.high != PL.arena.high || L.launches != PL.launches) return -7;
+  return 0;
+}
+
 MsmPlan plan_for(size_t n, size_t stride, int table, uint32_t c, uint32_t S, uint32_t G, uint32_t logm, int is_mont) {
   MsmPlan p;
   p.n = (uint32_t)n;
@@ -100,10 +137,9 @@ int emul_msm(int curve, int table, uint32_t c, uint32_t S, uint32_t G, uint32_t 
   std::memcpy(sc.data(), scalars, n * 32);
   jac_t out;
   ScalarSet ss{{sc.data(), nullptr, nullptr, nullptr}};
-  if (curve == 0) msm_run<HostLaunch, Pallas, Fq>(L, p, pts.data(), ss, &out);
-  else msm_run<HostLaunch, Vesta, Fp>(L, p, pts.data(), ss, &out);
+  int rc = curve == 0 ? run_msm_arena<Pallas, Fq>(p, pts.data(), ss, &out) : run_msm_arena<Vesta, Fp>(p, pts.data(), ss, &out);
   std::memcpy(out96, &out, 96);
-  return 0;
+  return rc;
 }
 
 // batched MSM: k scalar vectors (lengths lens[j] <= n, concatenated in `scalars`) over the same n points
@@ -130,10 +166,10 @@ int emul_msm_batch(int curve, int table, uint32_t c, uint32_t S, const void* aff
   size_t off = 0;
   for (uint32_t j = 0; j < k; j++) { ss.v[j] = sc.data() + off; p.len[j] = lens[j]; off += lens[j]; }
   std::vector<jac_t> out(k);
-  if (curve == 0) msm_run<HostLaunch, Pallas, Fq>(L, p, pts.data(), ss, out.data());
-  else msm_run<HostLaunch, Vesta, Fp>(L, p, pts.data(), ss, out.data());
+  int rc = curve == 0 ? run_msm_arena<Pallas, Fq>(p, pts.data(), ss, out.data())
+                      : run_msm_arena<Vesta, Fp>(p, pts.data(), ss, out.data());
   std::memcpy(out96k, out.data(), 96 * (size_t)k);
-  return 0;
+  return rc;
 }
 
 // the host API's chunked schedule: stages 1-5 per point-range chunk into one bucket array, stages 6-7 once

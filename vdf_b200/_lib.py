@@ -27,6 +27,13 @@ PROTOTYPES = {
     "vdfgpu_set_stream": (c_int, [c_void_p]),
     "vdfgpu_synchronize": (c_int, []),
     "vdfgpu_launch_count": (c_uint64, []),
+    "vdfgpu_trim": (c_int, []),
+    "vdfgpu_dropin_cache_clear": (c_int, []),
+    "vdfgpu_dropin_cache_stats": (c_int, [POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64)]),
+    "vdfgpu_witness_bank_create": (c_int, [c_int, c_void_p, c_uint64, c_size_t, POINTER(c_void_p)]),
+    "vdfgpu_witness_bank_destroy": (c_int, [c_void_p]),
+    "vdfgpu_witness_bank_read": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p]),
+    "vdfgpu_running_commit_step": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vdfgpu_profile_enable": (c_int, [c_int]),
     "vdfgpu_profile_read": (c_int, [POINTER(c_double), c_int]),
     "vdfgpu_point_sum_dev": (c_int, [c_int, c_void_p, c_size_t, c_void_p]),

@@ -10,6 +10,9 @@
 namespace vdf {
 
 static thread_local std::string g_error;
+static thread_local cudaStream_t t_stream = nullptr;      // vdfgpu_set_stream: per calling thread
+static thread_local cudaEvent_t t_sync_ev = nullptr;   // this thread's own "end of my call" event
+static thread_local cudaEvent_t t_wait_ev = nullptr;   // what guarded() waits for after unlocking (or nullptr)
 
 Context& ctx() {
   static Context c;
@@ -17,6 +20,28 @@ Context& ctx() {
 }
 
 void set_error(const std::string& msg) { g_error = msg; }
+
+cudaStream_t cur_stream() { return t_stream ? t_stream : ctx().own_stream; }
+
+void sync_after_unlock(cudaStream_t s) {
+  if (!t_sync_ev) VDF_CUDA_CHECK(cudaEventCreateWithFlags(&t_sync_ev, cudaEventDisableTiming));
+  VDF_CUDA_CHECK(cudaEventRecord(t_sync_ev, s));
+  t_wait_ev = t_sync_ev;
+}
+
+void wait_pending_sync() {
+  cudaEvent_t ev = t_wait_ev;
+  if (!ev) return;
+  t_wait_ev = nullptr;
+  VDF_CUDA_CHECK(cudaEventSynchronize(ev));
+}
+
+static long env_long(const char* name, long dflt, long lo, long hi) {
+  const char* s = std::getenv(name);
+  if (!s || !*s) return dflt;
+  long v = std::atol(s);
+  return v < lo ? lo : (v > hi ? hi : v);
+}
 
 static void init_locked(int device) {
   Context& c = ctx();
@@ -40,19 +65,85 @@ static void init_locked(int device) {
   VDF_CUDA_CHECK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
   for (auto& e : c.chunk_ev) VDF_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   VDF_CUDA_CHECK(cudaEventCreateWithFlags(&c.start_ev, cudaEventDisableTiming));
-  // keep freed blocks in the stream-ordered pool: the MSM allocates its workspace per call
+  // keep freed blocks in the stream-ordered pool (staging buffers of the host entry points)
   cudaMemPool_t pool;
   VDF_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
   uint64_t threshold = UINT64_MAX;
   VDF_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
-  c.stream = c.own_stream;
   c.device = device;
   c.ready = true;
 }
 
 void require_ready() {
   if (!ctx().ready) init_locked(0);
-  VDF_CUDA_CHECK(cudaSetDevice(ctx().device));
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != ctx().device) VDF_CUDA_CHECK(cudaSetDevice(ctx().device));
+}
+
+// ---- workspaces --------------------------------------------------------------------------------------
+static void workspace_release(Workspace& w) {
+  if (w.block) {
+    cudaStreamSynchronize(w.stream);
+    cudaFree(w.block);
+  }
+  w.block = nullptr;
+  w.block_bytes = 0;
+}
+
+static void trim_locked() {
+  Context& c = ctx();
+  if (!c.ready) return;
+  cudaDeviceSynchronize();
+  for (auto& w : c.workspaces) workspace_release(*w);
+  c.workspaces.clear();
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, c.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+}
+
+static bool workspaces_enabled() { return env_long("VDFGPU_WORKSPACE", 1, 0, 1) != 0; }
+
+// the arena of `s`, holding at least `need` bytes, reset for a new call; nullptr when it cannot be had
+// (then the caller falls back to stream-ordered pool allocations)
+static Workspace* workspace_for(cudaStream_t s, size_t need, bool may_fail) {
+  Context& c = ctx();
+  Workspace* w = nullptr;
+  for (auto& p : c.workspaces)
+    if (p->stream == s) w = p.get();
+  if (!w) {
+    if (c.workspaces.size() >= 8) {   // evict the least recently used arena
+      size_t lru = 0;
+      for (size_t i = 1; i < c.workspaces.size(); i++)
+        if (c.workspaces[i]->last_use < c.workspaces[lru]->last_use) lru = i;
+      workspace_release(*c.workspaces[lru]);
+      c.workspaces.erase(c.workspaces.begin() + lru);
+    }
+    c.workspaces.emplace_back(new Workspace());
+    w = c.workspaces.back().get();
+    w->stream = s;
+  }
+  w->last_use = ++c.tick;
+  if (w->block_bytes < need) {
+    workspace_release(*w);
+    size_t want = need + need / 16;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      want = need;
+      e = cudaMalloc(&p, want);
+    }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      if (may_fail) return nullptr;
+      throw std::runtime_error("msm workspace: cudaMalloc of " + std::to_string(need >> 20) + " MiB failed: " +
+                               cudaGetErrorString(e));
+    }
+    w->block = reinterpret_cast<uint8_t*>(p);
+    w->block_bytes = want;
+  }
+  w->arena.base = w->block;
+  w->arena.reset(w->block_bytes);
+  return w;
 }
 
 // ---- MSM dispatch -----------------------------------------------------------------------------------
@@ -76,19 +167,14 @@ static MsmPlan make_plan(const vdfgpu_gens* g, size_t n, bool is_mont, uint32_t 
   const size_t s_min = E <= (1u << 21) ? 16 : 32;   // latency path: shorter serial chains per thread
   if (S < s_min) S = s_min;
   if (S > 128) S = 128;
-  p.S = (uint32_t)S;
-  if (const char* s = std::getenv("VDFGPU_MSM_S")) p.S = (uint32_t)std::atoi(s);
-  p.G = 16;
-  p.logm = 3;
-  if (const char* s = std::getenv("VDFGPU_MSM_G")) p.G = (uint32_t)std::atoi(s);
-  if (const char* s = std::getenv("VDFGPU_MSM_LOGM")) p.logm = (uint32_t)std::atoi(s);
-  p.rec_warp = 1;
-  if (const char* s = std::getenv("VDFGPU_MSM_RECWARP")) p.rec_warp = (uint32_t)std::atoi(s);
+  p.S = (uint32_t)env_long("VDFGPU_MSM_S", (long)S, 1, 1 << 20);
+  p.G = (uint32_t)env_long("VDFGPU_MSM_G", 16, 4, 1024);
+  p.logm = (uint32_t)env_long("VDFGPU_MSM_LOGM", 3, 1, 8);
+  p.rec_warp = (uint32_t)env_long("VDFGPU_MSM_RECWARP", 1, 0, 1);
   // batched-affine halving rounds (msm_affine.cuh): worth their fixed costs only in the throughput regime and
-  // while the buckets still hold >= 16 entries on average
+  // while the buckets still hold >= 12 entries on average
   p.affine_rounds = 0;
-  p.affine_K = 32;
-  if (E >= (1ull << 23) && E <= (1ull << 29)) {
+  if (E >= (1ull << 23)) {
     // measured on B200 (profiles/r1_experiments.md): -3 % at 2^20 points, -5 % at 2^22, -9 % at 2^24.  Halve while
     // a bucket keeps >= 12 entries on average and a round still has >= 4 M additions to pay for its fixed costs
     // (three small launches + one inversion latency); the XYZZ ranges finish the rest
@@ -96,21 +182,56 @@ static MsmPlan make_plan(const vdfgpu_gens* g, size_t n, bool is_mont, uint32_t 
     while (p.affine_rounds < 5 && (avg >> (p.affine_rounds + 1)) >= 12 && (E >> (p.affine_rounds + 1)) >= (4u << 20))
       p.affine_rounds++;
   }
-  if (const char* s = std::getenv("VDFGPU_MSM_AFFINE")) p.affine_rounds = (uint32_t)std::atoi(s);
-  if (const char* s = std::getenv("VDFGPU_MSM_AFFINE_K")) p.affine_K = (uint32_t)std::atoi(s);
-  if (p.affine_K < 1) p.affine_K = 1;
+  p.affine_rounds = (uint32_t)env_long("VDFGPU_MSM_AFFINE", (long)p.affine_rounds, 0, 16);
+  p.affine_K = (uint32_t)env_long("VDFGPU_MSM_AFFINE_K", 32, 1, 4096);
   if (E >= (1ull << 31)) p.affine_rounds = 0;   // 32-bit list positions, 0xffffffff reserved
   return p;
 }
 
-void msm_on_device(vdfgpu_gens* g, size_t first, const fe* d_scalars, size_t n, jac_t* d_out, bool is_mont) {
+template <class C, class SF>
+static size_t msm_workspace_bytes(const MsmPlan& p) {
+  PlanLaunch PL;
+  ScalarSet ss{{nullptr, nullptr, nullptr, nullptr}};
+  msm_run<PlanLaunch, C, SF>(PL, p, nullptr, ss, nullptr);
+  return PL.arena.high;
+}
+
+static size_t plan_bytes(int curve, const MsmPlan& p) {
+  return curve == VDFGPU_PALLAS ? msm_workspace_bytes<Pallas, Fq>(p) : msm_workspace_bytes<Vesta, Fp>(p);
+}
+
+// Workspace for one MSM on stream `s`.  The affine rounds need ~52 B per sorted entry on top of the sort's 12 B:
+// when that does not fit in what the device has left (2^26 points next to a 55 GB table and a second stream's
+// arena), the plan drops them rather than failing.
+static Workspace* plan_workspace(int curve, MsmPlan& p, cudaStream_t s) {
+  if (!workspaces_enabled()) return nullptr;
+  size_t need = plan_bytes(curve, p);
+  Workspace* w = workspace_for(s, need, p.affine_rounds != 0);
+  if (!w && p.affine_rounds) {
+    p.affine_rounds = 0;
+    need = plan_bytes(curve, p);
+    w = workspace_for(s, need, false);
+  }
+  return w;
+}
+
+static void check_refs(const MsmPlan& p, const vdfgpu_gens* g, size_t n) {
+  // point references are 31 bits (+ sign), sorted positions 32 bits
+  if ((uint64_t)p.W * (p.table ? g->n : n) >= (1ull << 31))
+    throw ArgError("msm: W * n exceeds the 31-bit point references (split the generator set, see vdfgpu.h)");
+  if ((uint64_t)p.W * n * p.batch >= (1ull << 32)) throw ArgError("msm: too many sorted entries for one pass");
+}
+
+void msm_on_device(vdfgpu_gens* g, size_t first, const fe* d_scalars, size_t n, jac_t* d_out, bool is_mont,
+                   cudaStream_t stream) {
   if (first + n > g->n) throw ArgError("msm: more scalars than generators");
   Context& c = ctx();
+  cudaStream_t st = stream ? stream : cur_stream();
   c.prof.n_marks = 0;
-  CudaLaunch L(c.stream, &c.prof);
   MsmPlan p = make_plan(g, n, is_mont);
-  // point references are 31 bits (+ sign), sorted positions 32 bits
-  if ((uint64_t)p.W * (p.table ? g->n : n) >= (1ull << 31)) throw ArgError("msm: n too large for 31-bit point references");
+  check_refs(p, g, n);
+  Workspace* w = n ? plan_workspace(g->curve, p, st) : nullptr;
+  CudaLaunch L(st, &c.prof, w ? &w->arena : nullptr);
   const affine_t* pts = g->pts + first;
   ScalarSet ss{{d_scalars, nullptr, nullptr, nullptr}};
   if (g->curve == VDFGPU_PALLAS) msm_run<CudaLaunch, Pallas, Fq>(L, p, pts, ss, d_out);
@@ -123,15 +244,16 @@ void msm_on_device(vdfgpu_gens* g, size_t first, const fe* d_scalars, size_t n, 
 // reduction and normalisation are paid once.  Result is identical to the single-pass MSM.
 void msm_host_chunked(vdfgpu_gens* g, const void* h_scalars, size_t n, jac_t* d_out, fe* d_scalars, int chunks) {
   Context& c = ctx();
+  cudaStream_t st = cur_stream();
   c.prof.n_marks = 0;
-  CudaLaunch L(c.stream, nullptr);
+  CudaLaunch L(st, nullptr);
   MsmPlan full = make_plan(g, n, true);
-  if ((uint64_t)full.W * (full.table ? g->n : n) >= (1ull << 31)) throw ArgError("msm: n too large for 31-bit point references");
+  check_refs(full, g, n);
   const size_t NBK = (size_t)full.NB * full.B;
-  DevBuf<xyzz_t> buckets(NBK, c.stream), chunk_buckets(NBK, c.stream);
+  DevBuf<xyzz_t> buckets(NBK, st), chunk_buckets(NBK, st);
   L.zero(buckets.p, NBK * sizeof(xyzz_t));
   // the copy stream must not run ahead of earlier work on the compute stream that may still read d_scalars
-  VDF_CUDA_CHECK(cudaEventRecord(c.start_ev, c.stream));
+  VDF_CUDA_CHECK(cudaEventRecord(c.start_ev, st));
   VDF_CUDA_CHECK(cudaStreamWaitEvent(c.copy_stream, c.start_ev, 0));
   const size_t per = (n + chunks - 1) / chunks;
   for (int k = 0; k < chunks; k++) {
@@ -142,7 +264,7 @@ void msm_host_chunked(vdfgpu_gens* g, const void* h_scalars, size_t n, jac_t* d_
   }
   for (int k = 0; k < chunks; k++) {
     size_t lo = (size_t)k * per, len = lo < n ? (lo + per <= n ? per : n - lo) : 0;
-    VDF_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.chunk_ev[k], 0));
+    VDF_CUDA_CHECK(cudaStreamWaitEvent(st, c.chunk_ev[k], 0));
     if (!len) continue;
     MsmPlan p = full;
     p.n = (uint32_t)len;
@@ -174,16 +296,17 @@ void msm_batch_on_device(vdfgpu_gens* g, const fe* const* d_scalars, const size_
     if (lens[j] > n) n = lens[j];
   }
   Context& c = ctx();
+  cudaStream_t st = cur_stream();
   c.prof.n_marks = 0;
-  CudaLaunch L(c.stream, &c.prof);
   MsmPlan p = make_plan(g, n, true, k);
-  if ((uint64_t)p.W * (p.table ? g->n : n) >= (1ull << 31) || (uint64_t)p.W * n * k >= (1ull << 32))
-    throw ArgError("msm_batch: too large");
+  check_refs(p, g, n);
   ScalarSet ss{{nullptr, nullptr, nullptr, nullptr}};
   for (uint32_t j = 0; j < k; j++) {
     ss.v[j] = d_scalars[j];
     p.len[j] = (uint32_t)lens[j];
   }
+  Workspace* w = n ? plan_workspace(g->curve, p, st) : nullptr;
+  CudaLaunch L(st, &c.prof, w ? &w->arena : nullptr);
   if (g->curve == VDFGPU_PALLAS) msm_run<CudaLaunch, Pallas, Fq>(L, p, g->pts, ss, d_out);
   else msm_run<CudaLaunch, Vesta, Fp>(L, p, g->pts, ss, d_out);
   c.launches += L.launches;
@@ -333,28 +456,42 @@ int vdfgpu_init(int device) {
   return guarded([&] { init_locked(device); });
 }
 
+static void dropin_clear_locked();
+
 int vdfgpu_shutdown(void) {
   return guarded([&] {
     Context& c = ctx();
     if (!c.ready) return;
-    cudaStreamSynchronize(c.stream);
+    VDF_CUDA_CHECK(cudaSetDevice(c.device));
+    cudaDeviceSynchronize();
+    dropin_clear_locked();
+    trim_locked();
     if (c.own_stream) cudaStreamDestroy(c.own_stream);
     if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
     for (auto& e : c.chunk_ev) { if (e) cudaEventDestroy(e); e = nullptr; }
     if (c.start_ev) cudaEventDestroy(c.start_ev);
     c.start_ev = nullptr;
     for (auto& sl : c.slots) {
-      if (sl.copied) cudaEventDestroy(sl.copied);
       if (sl.done) cudaEventDestroy(sl.done);
       if (sl.d_scalars) cudaFree(sl.d_scalars);
       if (sl.d_out) cudaFree(sl.d_out);
+      if (sl.stream) cudaStreamDestroy(sl.stream);
       sl = AsyncSlot();
     }
     c.copy_stream = nullptr;
     c.own_stream = nullptr;
-    c.stream = nullptr;
+    t_stream = nullptr;
     c.ready = false;
     c.device = -1;
+  });
+}
+
+int vdfgpu_trim(void) {
+  return guarded([&] {
+    for (auto& sl : ctx().slots)
+      if (sl.busy) throw StateError("vdfgpu_trim: an asynchronous MSM is still in flight");
+    if (ctx().ready) VDF_CUDA_CHECK(cudaSetDevice(ctx().device));
+    trim_locked();
   });
 }
 
@@ -371,19 +508,18 @@ const char* vdfgpu_version(void) { return "vdfgpu 0.1 (sm_100a)"; }
 int vdfgpu_set_stream(void* cuda_stream) {
   return guarded([&] {
     require_ready();
-    Context& c = ctx();
-    c.stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c.own_stream;
+    t_stream = reinterpret_cast<cudaStream_t>(cuda_stream);   // nullptr: back to the library stream
   });
 }
 
 int vdfgpu_synchronize(void) {
   return guarded([&] {
     require_ready();
-    VDF_CUDA_CHECK(cudaStreamSynchronize(ctx().stream));
+    sync_after_unlock(cur_stream());
   });
 }
 
-uint64_t vdfgpu_launch_count(void) { return ctx().launches; }
+uint64_t vdfgpu_launch_count(void) { return ctx().launches.load(); }
 
 int vdfgpu_profile_enable(int on) {
   return guarded([&] { ctx().prof.enabled = on != 0; });
@@ -415,13 +551,13 @@ int vdfgpu_gens_create(int curve, const void* points_affine72_host, size_t n, ui
     Context& c = ctx();
     vdfgpu_gens* g = gens_alloc(curve, n, flags, window_bits);
     try {
-      CudaLaunch L(c.stream);
-      DevBuf<uint8_t> raw(n * 72, c.stream);
-      h2d(raw.p, points_affine72_host, n * 72, c.stream);
+      CudaLaunch L(cur_stream());
+      DevBuf<uint8_t> raw(n * 72, cur_stream());
+      h2d(raw.p, points_affine72_host, n * 72, cur_stream());
       L.run<256>(n, RepackFn{raw.p, g->pts});
       if (flags & VDFGPU_GENS_TABLE) build_table(g, L);
       c.launches += L.launches;
-      VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+      sync_after_unlock(cur_stream());
     } catch (...) {
       cudaFree(g->pts);
       delete g;
@@ -439,11 +575,11 @@ int vdfgpu_gens_progression(int curve, const void* k0_le32, const void* d_le32, 
     Context& c = ctx();
     vdfgpu_gens* g = gens_alloc(curve, n, flags, window_bits);
     try {
-      CudaLaunch L(c.stream);
+      CudaLaunch L(cur_stream());
       fe k0, d;
       std::memcpy(k0.v, k0_le32, 32);
       std::memcpy(d.v, d_le32, 32);
-      DevBuf<ProgSetup> setup(1, c.stream);
+      DevBuf<ProgSetup> setup(1, cur_stream());
       size_t threads = (n + PROG_CH - 1) / PROG_CH;
       if (threads >= (1ull << 32)) throw ArgError("gens_progression: n too large");
       if (curve == VDFGPU_PALLAS) {
@@ -455,7 +591,7 @@ int vdfgpu_gens_progression(int curve, const void* k0_le32, const void* d_le32, 
       }
       if (flags & VDFGPU_GENS_TABLE) build_table(g, L);
       c.launches += L.launches;
-      VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+      sync_after_unlock(cur_stream());
     } catch (...) {
       cudaFree(g->pts);
       delete g;
@@ -471,12 +607,12 @@ int vdfgpu_gens_export(const vdfgpu_gens* g, size_t first, size_t count, void* p
     if (first + count > (size_t)g->W * g->n) throw ArgError("gens_export: range out of bounds");
     require_ready();
     Context& c = ctx();
-    CudaLaunch L(c.stream);
-    DevBuf<uint8_t> raw(count * 72, c.stream);
+    CudaLaunch L(cur_stream());
+    DevBuf<uint8_t> raw(count * 72, cur_stream());
     L.run<256>(count, UnpackFn{g->pts + first, raw.p});
-    d2h(points_affine72_host, raw.p, count * 72, c.stream);
+    d2h(points_affine72_host, raw.p, count * 72, cur_stream());
     c.launches += L.launches;
-    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    sync_after_unlock(cur_stream());
   });
 }
 
@@ -495,7 +631,11 @@ uint32_t vdfgpu_gens_affine_rounds(const vdfgpu_gens* g, size_t n) {
 int vdfgpu_gens_destroy(vdfgpu_gens* g) {
   return guarded([&] {
     if (!g) return;
-    if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+    if (g->refs > 0) throw StateError("gens_destroy: a running instance still uses this generator set (destroy it first)");
+    if (ctx().ready) {
+      VDF_CUDA_CHECK(cudaSetDevice(ctx().device));
+      cudaDeviceSynchronize();   // MSMs on any stream (asynchronous slots, other threads) may still read the points
+    }
     cudaFree(g->pts);
     delete g;
   });
@@ -508,8 +648,8 @@ int vdfgpu_msm(vdfgpu_gens* g, const void* scalars32_host, size_t n, void* out_p
     require_ready();
     Context& c = ctx();
     if (n > g->n) throw ArgError("msm: more scalars than generators");
-    DevBuf<fe> sc(n ? n : 1, c.stream);
-    DevBuf<jac_t> res(1, c.stream);
+    DevBuf<fe> sc(n ? n : 1, cur_stream());
+    DevBuf<jac_t> res(1, cur_stream());
     // Chunked schedule (H2D of chunk k+1 under the accumulation of chunk k): measured on B200 at n = 2^22 the
     // per-chunk fixed costs (sparser buckets, extra sort passes, bucket merge) cancel the ~1.2 ms of hidden
     // copy (14.1 ms with 1 or 2 chunks, 14.8 with 4), so the default stays one chunk; VDFGPU_MSM_CHUNKS overrides.
@@ -520,16 +660,18 @@ int vdfgpu_msm(vdfgpu_gens* g, const void* scalars32_host, size_t n, void* out_p
     if (chunks > 1 && n >= 1024) {
       msm_host_chunked(g, scalars32_host, n, res.p, sc.p, chunks);
     } else {
-      h2d(sc.p, scalars32_host, n * 32, c.stream);
+      h2d(sc.p, scalars32_host, n * 32, cur_stream());
       msm_on_device(g, 0, sc.p, n, res.p, true);
     }
-    d2h(out_point96_host, res.p, sizeof(jac_t), c.stream);
-    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    d2h(out_point96_host, res.p, sizeof(jac_t), cur_stream());
+    sync_after_unlock(cur_stream());
   });
 }
 
-// Asynchronous host-scalar MSM: the upload of one call's scalars (copy stream) overlaps the kernels of the
-// previous call (compute stream).  A caller with several independent commitments keeps 2 slots in flight.
+// Asynchronous host-scalar MSM.  Every slot owns a stream that carries its upload, kernels and read-back, so with
+// two slots in flight the upload of one call AND its latency-bound stages (inversions, record levels, bucket
+// reduction: ~2 ms of a 2^22-point MSM at < 10 % of the warp slots) run under the multiply-bound kernels of the
+// other.  Each stream has its own workspace arena.
 int vdfgpu_msm_submit(vdfgpu_gens* g, const void* scalars32_host, size_t n, void* out_point96_host, int slot) {
   return guarded([&] {
     if (!g || !out_point96_host || (n && !scalars32_host)) throw ArgError("msm_submit: null pointer");
@@ -539,24 +681,26 @@ int vdfgpu_msm_submit(vdfgpu_gens* g, const void* scalars32_host, size_t n, void
     Context& c = ctx();
     AsyncSlot& s = c.slots[slot];
     if (s.busy) throw StateError("msm_submit: slot still in flight (call vdfgpu_msm_wait first)");
-    if (!s.copied) {
-      VDF_CUDA_CHECK(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+    if (!s.stream) {
+      VDF_CUDA_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
       VDF_CUDA_CHECK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
       VDF_CUDA_CHECK(cudaMalloc((void**)&s.d_out, sizeof(jac_t)));
     }
     if (s.cap < n) {
+      VDF_CUDA_CHECK(cudaStreamSynchronize(s.stream));
       if (s.d_scalars) VDF_CUDA_CHECK(cudaFree(s.d_scalars));
       s.d_scalars = nullptr;
+      s.cap = 0;
       VDF_CUDA_CHECK(cudaMalloc((void**)&s.d_scalars, (n ? n : 1) * sizeof(fe)));
       s.cap = n;
     }
-    // the slot is idle, so nothing on the compute stream still reads its buffers
-    if (n) VDF_CUDA_CHECK(cudaMemcpyAsync(s.d_scalars, scalars32_host, n * 32, cudaMemcpyHostToDevice, c.copy_stream));
-    VDF_CUDA_CHECK(cudaEventRecord(s.copied, c.copy_stream));
-    VDF_CUDA_CHECK(cudaStreamWaitEvent(c.stream, s.copied, 0));
-    msm_on_device(g, 0, s.d_scalars, n, s.d_out, true);
-    VDF_CUDA_CHECK(cudaMemcpyAsync(out_point96_host, s.d_out, sizeof(jac_t), cudaMemcpyDeviceToHost, c.stream));
-    VDF_CUDA_CHECK(cudaEventRecord(s.done, c.stream));
+    // the generator set may have been built on the caller's stream just before: order the slot behind it
+    VDF_CUDA_CHECK(cudaEventRecord(c.start_ev, cur_stream()));
+    VDF_CUDA_CHECK(cudaStreamWaitEvent(s.stream, c.start_ev, 0));
+    if (n) VDF_CUDA_CHECK(cudaMemcpyAsync(s.d_scalars, scalars32_host, n * 32, cudaMemcpyHostToDevice, s.stream));
+    msm_on_device(g, 0, s.d_scalars, n, s.d_out, true, s.stream);
+    VDF_CUDA_CHECK(cudaMemcpyAsync(out_point96_host, s.d_out, sizeof(jac_t), cudaMemcpyDeviceToHost, s.stream));
+    VDF_CUDA_CHECK(cudaEventRecord(s.done, s.stream));
     s.busy = true;
   });
 }
@@ -567,7 +711,7 @@ int vdfgpu_msm_wait(int slot) {
     require_ready();
     AsyncSlot& s = ctx().slots[slot];
     if (!s.busy) throw StateError("msm_wait: nothing in flight in this slot");
-    VDF_CUDA_CHECK(cudaEventSynchronize(s.done));
+    t_wait_ev = s.done;   // waited for after the context mutex is released
     s.busy = false;
   });
 }
@@ -609,15 +753,15 @@ int vdfgpu_point_sum(int curve, const void* points96_host, size_t k, void* out_p
     if (curve != VDFGPU_PALLAS && curve != VDFGPU_VESTA) throw ArgError("point_sum: unknown curve");
     require_ready();
     Context& c = ctx();
-    CudaLaunch L(c.stream);
-    DevBuf<jac_t> in(k ? k : 1, c.stream);
-    DevBuf<jac_t> res(1, c.stream);
-    h2d(in.p, points96_host, k * sizeof(jac_t), c.stream);
-    if (curve == VDFGPU_PALLAS) L.run<32>(1, JacSumFn<Pallas>{in.p, (uint32_t)k, res.p});
-    else L.run<32>(1, JacSumFn<Vesta>{in.p, (uint32_t)k, res.p});
-    d2h(out_point96_host, res.p, sizeof(jac_t), c.stream);
+    CudaLaunch L(cur_stream());
+    DevBuf<jac_t> in(k ? k : 1, cur_stream());
+    DevBuf<jac_t> res(1, cur_stream());
+    h2d(in.p, points96_host, k * sizeof(jac_t), cur_stream());
+    if (curve == VDFGPU_PALLAS) L.run<32>(32, JacSumFn<Pallas>{in.p, (uint32_t)k, res.p});
+    else L.run<32>(32, JacSumFn<Vesta>{in.p, (uint32_t)k, res.p});
+    d2h(out_point96_host, res.p, sizeof(jac_t), cur_stream());
     c.launches += L.launches;
-    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    sync_after_unlock(cur_stream());
   });
 }
 
@@ -627,46 +771,209 @@ int vdfgpu_point_sum_dev(int curve, const void* points96_dev, size_t k, void* ou
     if (curve != VDFGPU_PALLAS && curve != VDFGPU_VESTA) throw ArgError("point_sum_dev: unknown curve");
     require_ready();
     Context& c = ctx();
-    CudaLaunch L(c.stream);
+    CudaLaunch L(cur_stream());
     const jac_t* in = reinterpret_cast<const jac_t*>(points96_dev);
     jac_t* out = reinterpret_cast<jac_t*>(out_point96_dev);
-    if (curve == VDFGPU_PALLAS) L.run<32>(1, JacSumFn<Pallas>{in, (uint32_t)k, out});
-    else L.run<32>(1, JacSumFn<Vesta>{in, (uint32_t)k, out});
+    if (curve == VDFGPU_PALLAS) L.run<32>(32, JacSumFn<Pallas>{in, (uint32_t)k, out});
+    else L.run<32>(32, JacSumFn<Vesta>{in, (uint32_t)k, out});
     c.launches += L.launches;
   });
 }
 
-static void mult_pippenger(int curve, void* out, const void* points, size_t npoints, const void* scalars,
-                           bool is_mont) {
-  int rc = guarded([&] {
-    if (!out || (npoints && (!points || !scalars))) throw ArgError("mult_pippenger: null pointer");
-    require_ready();
-    Context& c = ctx();
-    if (npoints == 0) {
-      std::memset(out, 0, 96);
-      return;
+// ---- drop-in cache behind mult_pippenger_{pallas,vesta} ----------------------------------------------------
+// pasta-msm's entry point receives the points with every call, but its only caller on this path, nova's
+// commit(), passes the SAME generators every time (fixed for the life of PublicParams, src/nova/proof.rs:232-237;
+// commit(W) and commit(T) use prefixes of one Vec).  So the first call with a new (curve, host pointer) uploads and
+// repacks the points, builds the window table and keeps the set resident; later calls with that pointer and
+// npoints <= the cached length upload only the scalars and take the same path as vdfgpu_msm().
+// A cached set is trusted only while a sample of the caller's points still matches byte for byte (x, y and the
+// infinity flag of ~530 points: the first and last 8 and an even stride); VDFGPU_DROPIN_VERIFY=full hashes every
+// point on every call instead (exact, ~70 ms per 2^22 points of host time), =off trusts pointer + length.
+// VDFGPU_DROPIN_CACHE=0 disables the cache (every call is one-shot), VDFGPU_DROPIN_ENTRIES bounds it (LRU, default 4).
+static constexpr size_t DROPIN_MIN_POINTS = 1024;   // below this the one-shot path is as fast
+
+static std::vector<size_t> dropin_sample_indices(size_t n) {
+  std::vector<size_t> idx;
+  const size_t edge = 8, strided = 512;
+  for (size_t i = 0; i < edge && i < n; i++) idx.push_back(i);
+  const size_t step = n / strided ? n / strided : 1;
+  for (size_t i = edge; i + edge < n; i += step) idx.push_back(i);
+  for (size_t i = n > 2 * edge ? n - edge : (n > edge ? edge : n); i < n; i++) idx.push_back(i);
+  return idx;
+}
+
+static uint64_t dropin_full_hash(const uint8_t* pts72, size_t n) {
+  uint64_t h = 0x9e3779b97f4a7c15ull;
+  for (size_t i = 0; i < n; i++) {
+    uint64_t w[9];
+    std::memcpy(w, pts72 + i * 72, 72);
+    w[8] &= 0xffull;   // the 7 padding bytes of the repr(C) struct are indeterminate
+    for (int k = 0; k < 9; k++) {
+      h ^= w[k];
+      h *= 0xff51afd7ed558ccdull;
+      h ^= h >> 29;
     }
+  }
+  return h;
+}
+
+static int dropin_verify_mode() {   // 0 off, 1 sample, 2 full
+  const char* s = std::getenv("VDFGPU_DROPIN_VERIFY");
+  if (!s) return 1;
+  if (!std::strcmp(s, "off")) return 0;
+  if (!std::strcmp(s, "full")) return 2;
+  return 1;
+}
+
+static void dropin_drop(DropinEntry& e) {
+  if (e.gens) {
+    cudaFree(e.gens->pts);
+    delete e.gens;
+    e.gens = nullptr;
+  }
+}
+
+static void dropin_clear_locked() {
+  Context& c = ctx();
+  if (c.dropin.empty()) return;
+  if (c.ready) cudaDeviceSynchronize();
+  for (auto& e : c.dropin) dropin_drop(e);
+  c.dropin.clear();
+}
+
+static bool dropin_matches(const DropinEntry& e, int curve, const uint8_t* pts72, size_t npoints, int mode) {
+  if (e.curve != curve || e.host_ptr != pts72 || npoints > e.n) return false;
+  if (mode == 0) return true;
+  if (mode == 2) return npoints == e.n && dropin_full_hash(pts72, npoints) == e.full_hash;
+  for (size_t k = 0; k < e.sample_idx.size(); k++) {
+    const size_t i = e.sample_idx[k];
+    if (i >= npoints) break;
+    if (std::memcmp(pts72 + i * 72, &e.sample_bytes[k * 65], 65) != 0) return false;
+  }
+  return true;
+}
+
+// resident generator set for this call's points, or nullptr: take the one-shot path
+static vdfgpu_gens* dropin_lookup(int curve, const void* points, size_t npoints) {
+  Context& c = ctx();
+  if (npoints < DROPIN_MIN_POINTS || env_long("VDFGPU_DROPIN_CACHE", 1, 0, 1) == 0) return nullptr;
+  const uint8_t* pts72 = reinterpret_cast<const uint8_t*>(points);
+  const int mode = dropin_verify_mode();
+  for (size_t k = 0; k < c.dropin.size(); k++) {
+    DropinEntry& e = c.dropin[k];
+    if (e.curve != curve || e.host_ptr != points) continue;
+    if (dropin_matches(e, curve, pts72, npoints, mode)) {
+      e.last_use = ++c.tick;
+      c.dropin_hits++;
+      return e.gens;
+    }
+    // same address, other contents or a longer slice: the cached set is stale
+    cudaDeviceSynchronize();
+    dropin_drop(e);
+    c.dropin.erase(c.dropin.begin() + k);
+    break;
+  }
+  c.dropin_misses++;
+  const size_t max_entries = (size_t)env_long("VDFGPU_DROPIN_ENTRIES", 4, 1, 64);
+  while (c.dropin.size() >= max_entries) {
+    size_t lru = 0;
+    for (size_t i = 1; i < c.dropin.size(); i++)
+      if (c.dropin[i].last_use < c.dropin[lru].last_use) lru = i;
+    cudaDeviceSynchronize();
+    dropin_drop(c.dropin[lru]);
+    c.dropin.erase(c.dropin.begin() + lru);
+  }
+  // window table when it fits comfortably (W levels of 64 B per point), plain resident points otherwise
+  uint32_t flags = VDFGPU_GENS_TABLE;
+  size_t free_b = 0, total_b = 0;
+  VDF_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+  const uint32_t c_bits = msm_pick_c(npoints, true);
+  if ((uint64_t)msm_windows(c_bits) * npoints >= (1ull << 31) ||
+      (size_t)msm_windows(c_bits) * npoints * sizeof(affine_t) > free_b / 3)
+    flags = 0;
+  vdfgpu_gens* g = gens_alloc(curve, npoints, flags, 0);
+  cudaStream_t st = cur_stream();
+  try {
+    CudaLaunch L(st);
+    DevBuf<uint8_t> raw(npoints * 72, st);
+    h2d(raw.p, points, npoints * 72, st);
+    L.run<256>(npoints, RepackFn{raw.p, g->pts});
+    if (flags & VDFGPU_GENS_TABLE) build_table(g, L);
+    c.launches += L.launches;
+  } catch (...) {
+    cudaFree(g->pts);
+    delete g;
+    throw;
+  }
+  DropinEntry e;
+  e.curve = curve;
+  e.host_ptr = points;
+  e.n = npoints;
+  e.sample_idx = dropin_sample_indices(npoints);
+  e.sample_bytes.resize(e.sample_idx.size() * 65);
+  for (size_t k = 0; k < e.sample_idx.size(); k++)
+    std::memcpy(&e.sample_bytes[k * 65], pts72 + e.sample_idx[k] * 72, 65);
+  if (mode == 2) e.full_hash = dropin_full_hash(pts72, npoints);
+  e.gens = g;
+  e.last_use = ++c.tick;
+  c.dropin.push_back(std::move(e));
+  return g;
+}
+
+static void mult_pippenger_body(int curve, void* out, const void* points, size_t npoints, const void* scalars,
+                                bool is_mont) {
+  require_ready();
+  Context& c = ctx();
+  cudaStream_t st = cur_stream();
+  DevBuf<fe> sc(npoints, st);
+  DevBuf<jac_t> res(1, st);
+  h2d(sc.p, scalars, npoints * 32, st);
+  if (vdfgpu_gens* cached = dropin_lookup(curve, points, npoints)) {
+    msm_on_device(cached, 0, sc.p, npoints, res.p, is_mont);
+  } else {
     vdfgpu_gens g;
     g.curve = curve;
     g.n = npoints;
     g.flags = 0;
     g.W = 1;
-    CudaLaunch L(c.stream);
-    DevBuf<uint8_t> raw(npoints * 72, c.stream);
-    DevBuf<affine_t> pts(npoints, c.stream);
-    DevBuf<fe> sc(npoints, c.stream);
-    DevBuf<jac_t> res(1, c.stream);
-    h2d(raw.p, points, npoints * 72, c.stream);
-    h2d(sc.p, scalars, npoints * 32, c.stream);
+    CudaLaunch L(st);
+    DevBuf<uint8_t> raw(npoints * 72, st);
+    DevBuf<affine_t> pts(npoints, st);
+    h2d(raw.p, points, npoints * 72, st);
     L.run<256>(npoints, RepackFn{raw.p, pts.p});
     c.launches += L.launches;
     g.pts = pts.p;
     msm_on_device(&g, 0, sc.p, npoints, res.p, is_mont);
-    d2h(out, res.p, sizeof(jac_t), c.stream);
-    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
-  });
+  }
+  d2h(out, res.p, sizeof(jac_t), st);
+  sync_after_unlock(st);
+}
+
+static void mult_pippenger(int curve, void* out, const void* points, size_t npoints, const void* scalars,
+                           bool is_mont) {
+  // pasta-msm's entry point is infallible (void) and its Rust wrapper asserts points.len() == scalars.len().
+  // Argument misuse: say so and return the identity.  A CUDA failure (typically out of memory): drop every cached
+  // set and workspace, trim the pool and retry once; only a second failure aborts, as the reference would panic.
+  if (!out) {
+    std::fprintf(stderr, "mult_pippenger: null output pointer\n");
+    return;
+  }
+  if (npoints == 0 || !points || !scalars) {
+    if (npoints) std::fprintf(stderr, "mult_pippenger: null points/scalars with npoints = %zu; returning the identity\n", npoints);
+    std::memset(out, 0, 96);
+    return;
+  }
+  int rc = guarded([&] { mult_pippenger_body(curve, out, points, npoints, scalars, is_mont); });
+  if (rc == VDFGPU_ERR_CUDA) {
+    std::fprintf(stderr, "mult_pippenger: %s -- releasing cached sets and workspaces, retrying once\n", vdfgpu_last_error());
+    guarded([&] {
+      cudaGetLastError();
+      dropin_clear_locked();
+      trim_locked();
+    });
+    rc = guarded([&] { mult_pippenger_body(curve, out, points, npoints, scalars, is_mont); });
+  }
   if (rc != VDFGPU_OK) {
-    // pasta-msm's entry point is infallible (void); its Rust wrapper panics on misuse.  Mirror that.
     std::fprintf(stderr, "mult_pippenger: %s\n", vdfgpu_last_error());
     std::abort();
   }
@@ -680,6 +987,19 @@ void mult_pippenger_vesta(void* out, const void* points, size_t npoints, const v
   mult_pippenger(VDFGPU_VESTA, out, points, npoints, scalars, is_mont);
 }
 
+int vdfgpu_dropin_cache_clear(void) {
+  return guarded([&] { dropin_clear_locked(); });
+}
+
+int vdfgpu_dropin_cache_stats(uint64_t* hits, uint64_t* misses, uint64_t* entries) {
+  return guarded([&] {
+    Context& c = ctx();
+    if (hits) *hits = c.dropin_hits;
+    if (misses) *misses = c.dropin_misses;
+    if (entries) *entries = c.dropin.size();
+  });
+}
+
 // ---- batched MinRoot verification -----------------------------------------------------------------------
 int vdfgpu_minroot_check_batch_dev(int field, const void* results_dev, const void* originals_dev,
                                    const uint64_t* t_each_dev, uint64_t t_uniform, size_t n,
@@ -689,7 +1009,7 @@ int vdfgpu_minroot_check_batch_dev(int field, const void* results_dev, const voi
     if (n && (!results_dev || !originals_dev || !ok_out_dev)) throw ArgError("minroot_check: null pointer");
     require_ready();
     Context& c = ctx();
-    CudaLaunch L(c.stream);
+    CudaLaunch L(cur_stream());
     if (field == VDFGPU_FP) minroot_check_dispatch<Fp>(L, results_dev, originals_dev, t_each_dev, t_uniform, n, ok_out_dev);
     else minroot_check_dispatch<Fq>(L, results_dev, originals_dev, t_each_dev, t_uniform, n, ok_out_dev);
     c.launches += L.launches;
@@ -704,19 +1024,19 @@ int vdfgpu_minroot_check_batch(int field, const void* results_host, const void* 
     if (n == 0) return;
     require_ready();
     Context& c = ctx();
-    CudaLaunch L(c.stream);
-    DevBuf<state_t> res(n, c.stream), orig(n, c.stream);
-    DevBuf<uint64_t> tt(t_each ? n : 1, c.stream);
-    DevBuf<uint8_t> ok(n, c.stream);
-    h2d(res.p, results_host, n * sizeof(state_t), c.stream);
-    h2d(orig.p, originals_host, n * sizeof(state_t), c.stream);
-    if (t_each) h2d(tt.p, t_each, n * 8, c.stream);
+    CudaLaunch L(cur_stream());
+    DevBuf<state_t> res(n, cur_stream()), orig(n, cur_stream());
+    DevBuf<uint64_t> tt(t_each ? n : 1, cur_stream());
+    DevBuf<uint8_t> ok(n, cur_stream());
+    h2d(res.p, results_host, n * sizeof(state_t), cur_stream());
+    h2d(orig.p, originals_host, n * sizeof(state_t), cur_stream());
+    if (t_each) h2d(tt.p, t_each, n * 8, cur_stream());
     const uint64_t* tp = t_each ? tt.p : nullptr;
     if (field == VDFGPU_FP) minroot_check_dispatch<Fp>(L, res.p, orig.p, tp, t_uniform, n, ok.p);
     else minroot_check_dispatch<Fq>(L, res.p, orig.p, tp, t_uniform, n, ok.p);
-    d2h(ok_out_host, ok.p, n, c.stream);
+    d2h(ok_out_host, ok.p, n, cur_stream());
     c.launches += L.launches;
-    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    sync_after_unlock(cur_stream());
   });
 }
 
@@ -728,14 +1048,14 @@ int vdfgpu_minroot_inverse_eval_batch(int field, const void* results_host, uint6
     if (n == 0) return;
     require_ready();
     Context& c = ctx();
-    CudaLaunch L(c.stream);
-    DevBuf<state_t> res(n, c.stream), out(n, c.stream);
-    h2d(res.p, results_host, n * sizeof(state_t), c.stream);
+    CudaLaunch L(cur_stream());
+    DevBuf<state_t> res(n, cur_stream()), out(n, cur_stream());
+    h2d(res.p, results_host, n * sizeof(state_t), cur_stream());
     if (field == VDFGPU_FP) L.run<128>(n, MinRootInverseEvalFn<Fp>{res.p, t, out.p});
     else L.run<128>(n, MinRootInverseEvalFn<Fq>{res.p, t, out.p});
-    d2h(out_host, out.p, n * sizeof(state_t), c.stream);
+    d2h(out_host, out.p, n * sizeof(state_t), cur_stream());
     c.launches += L.launches;
-    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    sync_after_unlock(cur_stream());
   });
 }
 
@@ -746,16 +1066,16 @@ int vdfgpu_minroot_witness_batch(int field, const void* results_host, uint64_t t
     if (n == 0) return;
     require_ready();
     Context& c = ctx();
-    CudaLaunch L(c.stream);
+    CudaLaunch L(cur_stream());
     const size_t per = 4 * (size_t)t + 1;
-    DevBuf<state_t> res(n, c.stream);
-    DevBuf<fe> out(n * per, c.stream);
-    h2d(res.p, results_host, n * sizeof(state_t), c.stream);
+    DevBuf<state_t> res(n, cur_stream());
+    DevBuf<fe> out(n * per, cur_stream());
+    h2d(res.p, results_host, n * sizeof(state_t), cur_stream());
     if (field == VDFGPU_FP) L.run<128>(n, MinRootWitnessFn<Fp>{res.p, t, out.p});
     else L.run<128>(n, MinRootWitnessFn<Fq>{res.p, t, out.p});
-    d2h(out_host, out.p, n * per * 32, c.stream);
+    d2h(out_host, out.p, n * per * 32, cur_stream());
     c.launches += L.launches;
-    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    sync_after_unlock(cur_stream());
   });
 }
 
@@ -768,15 +1088,15 @@ int vdfgpu_field_mul_batch(int field, const void* a_host, const void* b_host, si
     if (n == 0) return;
     require_ready();
     Context& c = ctx();
-    CudaLaunch L(c.stream);
-    DevBuf<fe> a(n, c.stream), b(n, c.stream), o(n, c.stream);
-    h2d(a.p, a_host, n * 32, c.stream);
-    h2d(b.p, b_host, n * 32, c.stream);
+    CudaLaunch L(cur_stream());
+    DevBuf<fe> a(n, cur_stream()), b(n, cur_stream()), o(n, cur_stream());
+    h2d(a.p, a_host, n * 32, cur_stream());
+    h2d(b.p, b_host, n * 32, cur_stream());
     if (field == VDFGPU_FP) L.run<256>(n, FieldMulFn<Fp>{a.p, b.p, o.p, iters});
     else L.run<256>(n, FieldMulFn<Fq>{a.p, b.p, o.p, iters});
-    d2h(out_host, o.p, n * 32, c.stream);
+    d2h(out_host, o.p, n * 32, cur_stream());
     c.launches += L.launches;
-    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    sync_after_unlock(cur_stream());
   });
 }
 
@@ -784,10 +1104,10 @@ int vdfgpu_imad_peak(double* mul32_per_s_wide, double* imad_per_s_lo, double* ia
   return guarded([&] {
     require_ready();
     Context& c = ctx();
-    DevBuf<uint32_t> sink(4, c.stream);
-    double w = probe_rate<0>(c.stream, sink.p);
-    double l = probe_rate<1>(c.stream, sink.p);
-    double a = probe_rate<2>(c.stream, sink.p);
+    DevBuf<uint32_t> sink(4, cur_stream());
+    double w = probe_rate<0>(cur_stream(), sink.p);
+    double l = probe_rate<1>(cur_stream(), sink.p);
+    double a = probe_rate<2>(cur_stream(), sink.p);
     c.launches += 9;
     if (mul32_per_s_wide) *mul32_per_s_wide = w;
     if (imad_per_s_lo) *imad_per_s_lo = l;

@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "ctx.cuh"
+#include "minroot.cuh"
 #include "r1cs.cuh"
 #include "r1cs_host.hpp"
 
@@ -14,6 +15,7 @@ struct vdfgpu_r1cs {
   uint32_t* row_ptr = nullptr;  // [3*cons+1]
   uint32_t* col = nullptr;
   vdf::fe* val = nullptr;
+  mutable int refs = 0;   // running instances holding this shape (vdfgpu_r1cs_destroy refuses while > 0)
   vdf::CsrView view() const { return vdf::CsrView{row_ptr, col, val, cons, vars, io}; }
 };
 
@@ -29,6 +31,16 @@ struct vdfgpu_running {
   vdf::fe* r = nullptr;   // challenge
   vdf::jac_t* comm = nullptr;  // [2] comm_W2, comm_T
   bool have_running = false, have_fresh = false;
+};
+
+// Step-circuit witnesses of all n steps of one proof, generated on the device on a side stream
+struct vdfgpu_witness_bank {
+  int field = 0;
+  uint64_t t = 0;
+  size_t n = 0;
+  vdf::fe* w = nullptr;         // [n][4t + 1]
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ready = nullptr;
 };
 
 namespace vdf {
@@ -114,10 +126,10 @@ int vdfgpu_r1cs_create(int field, size_t num_cons, size_t num_vars, size_t num_i
       VDF_CUDA_CHECK(cudaMalloc((void**)&s->row_ptr, (R + 1) * 4));
       VDF_CUDA_CHECK(cudaMalloc((void**)&s->col, (nnz ? nnz : 1) * 4));
       VDF_CUDA_CHECK(cudaMalloc((void**)&s->val, (nnz ? nnz : 1) * 32));
-      h2d(s->row_ptr, row_ptr.data(), (R + 1) * 4, c.stream);
-      h2d(s->col, col.data(), nnz * 4, c.stream);
-      h2d(s->val, val.data(), nnz * 32, c.stream);
-      VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+      h2d(s->row_ptr, row_ptr.data(), (R + 1) * 4, cur_stream());
+      h2d(s->col, col.data(), nnz * 4, cur_stream());
+      h2d(s->val, val.data(), nnz * 32, cur_stream());
+      sync_after_unlock(cur_stream());
     } catch (...) {
       cudaFree(s->row_ptr); cudaFree(s->col); cudaFree(s->val);
       delete s;
@@ -130,7 +142,11 @@ int vdfgpu_r1cs_create(int field, size_t num_cons, size_t num_vars, size_t num_i
 int vdfgpu_r1cs_destroy(vdfgpu_r1cs* s) {
   return guarded([&] {
     if (!s) return;
-    if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+    if (s->refs > 0) throw StateError("r1cs_destroy: a running instance still uses this shape (destroy it first)");
+    if (ctx().ready) {
+      VDF_CUDA_CHECK(cudaSetDevice(ctx().device));
+      cudaDeviceSynchronize();
+    }
     cudaFree(s->row_ptr); cudaFree(s->col); cudaFree(s->val);
     delete s;
   });
@@ -141,17 +157,17 @@ int vdfgpu_multiply_vec(const vdfgpu_r1cs* s, const void* z_host, void* Az_host,
     if (!s || !z_host || !Az_host || !Bz_host || !Cz_host) throw ArgError("multiply_vec: null pointer");
     require_ready();
     Context& c = ctx();
-    CudaLaunch L(c.stream);
+    CudaLaunch L(cur_stream());
     size_t nz = (size_t)s->vars + 1 + s->io;
-    DevBuf<fe> z(nz, c.stream), out(3 * (size_t)s->cons, c.stream);
-    h2d(z.p, z_host, nz * 32, c.stream);
+    DevBuf<fe> z(nz, cur_stream()), out(3 * (size_t)s->cons, cur_stream());
+    h2d(z.p, z_host, nz * 32, cur_stream());
     ZView zv{z.p, z.p + s->vars, z.p + s->vars + 1};
     launch_multiply_vec(L, s, zv, out.p, out.p + s->cons, out.p + 2 * (size_t)s->cons);
-    d2h(Az_host, out.p, (size_t)s->cons * 32, c.stream);
-    d2h(Bz_host, out.p + s->cons, (size_t)s->cons * 32, c.stream);
-    d2h(Cz_host, out.p + 2 * (size_t)s->cons, (size_t)s->cons * 32, c.stream);
+    d2h(Az_host, out.p, (size_t)s->cons * 32, cur_stream());
+    d2h(Bz_host, out.p + s->cons, (size_t)s->cons * 32, cur_stream());
+    d2h(Cz_host, out.p + 2 * (size_t)s->cons, (size_t)s->cons * 32, cur_stream());
     c.launches += L.launches;
-    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    sync_after_unlock(cur_stream());
   });
 }
 
@@ -168,26 +184,26 @@ int vdfgpu_commit_T(const vdfgpu_r1cs* s, vdfgpu_gens* gens, const void* W1_host
     }
     require_ready();
     Context& c = ctx();
-    CudaLaunch L(c.stream);
+    CudaLaunch L(cur_stream());
     const size_t nv = s->vars, io = s->io, nc = s->cons;
-    DevBuf<fe> W1(nv ? nv : 1, c.stream), W2(nv ? nv : 1, c.stream), uX1(1 + io, c.stream), uX2(1 + io, c.stream);
-    DevBuf<fe> T(nc, c.stream);
-    DevBuf<jac_t> comm(1, c.stream);
-    h2d(W1.p, W1_host, nv * 32, c.stream);
-    h2d(W2.p, W2_host, nv * 32, c.stream);
-    h2d(uX1.p, u1_host, 32, c.stream);
-    h2d(uX1.p + 1, X1_host, io * 32, c.stream);
+    DevBuf<fe> W1(nv ? nv : 1, cur_stream()), W2(nv ? nv : 1, cur_stream()), uX1(1 + io, cur_stream()), uX2(1 + io, cur_stream());
+    DevBuf<fe> T(nc, cur_stream());
+    DevBuf<jac_t> comm(1, cur_stream());
+    h2d(W1.p, W1_host, nv * 32, cur_stream());
+    h2d(W2.p, W2_host, nv * 32, cur_stream());
+    h2d(uX1.p, u1_host, 32, cur_stream());
+    h2d(uX1.p + 1, X1_host, io * 32, cur_stream());
     fe one = host_one(s->field);
-    h2d(uX2.p, &one, 32, c.stream);  // u2 = 1 (fresh instance); pageable 32-byte copy is staged by the driver
-    h2d(uX2.p + 1, X2_host, io * 32, c.stream);
+    h2d(uX2.p, &one, 32, cur_stream());  // u2 = 1 (fresh instance); pageable 32-byte copy is staged by the driver
+    h2d(uX2.p + 1, X2_host, io * 32, cur_stream());
     launch_cross_term(L, s, ZView{W1.p, uX1.p, uX1.p + 1}, ZView{W2.p, uX2.p, uX2.p + 1}, T.p);
     c.launches += L.launches;
     if (gens) {
       msm_on_device(gens, 0, T.p, nc, comm.p, true);
-      d2h(comm_T_point96_host, comm.p, sizeof(jac_t), c.stream);
+      d2h(comm_T_point96_host, comm.p, sizeof(jac_t), cur_stream());
     }
-    if (T_host) d2h(T_host, T.p, nc * 32, c.stream);
-    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    if (T_host) d2h(T_host, T.p, nc * 32, cur_stream());
+    sync_after_unlock(cur_stream());
   });
 }
 
@@ -199,18 +215,18 @@ int vdfgpu_fold(int field, void* W1_host, const void* W2_host, size_t nW, void* 
     if (nW + nE == 0) return;
     require_ready();
     Context& c = ctx();
-    CudaLaunch L(c.stream);
-    DevBuf<fe> W1(nW ? nW : 1, c.stream), W2(nW ? nW : 1, c.stream), E1(nE ? nE : 1, c.stream), T(nE ? nE : 1, c.stream), r(1, c.stream);
-    h2d(W1.p, W1_host, nW * 32, c.stream);
-    h2d(W2.p, W2_host, nW * 32, c.stream);
-    h2d(E1.p, E1_host, nE * 32, c.stream);
-    h2d(T.p, T_host, nE * 32, c.stream);
-    h2d(r.p, r32_host, 32, c.stream);
+    CudaLaunch L(cur_stream());
+    DevBuf<fe> W1(nW ? nW : 1, cur_stream()), W2(nW ? nW : 1, cur_stream()), E1(nE ? nE : 1, cur_stream()), T(nE ? nE : 1, cur_stream()), r(1, cur_stream());
+    h2d(W1.p, W1_host, nW * 32, cur_stream());
+    h2d(W2.p, W2_host, nW * 32, cur_stream());
+    h2d(E1.p, E1_host, nE * 32, cur_stream());
+    h2d(T.p, T_host, nE * 32, cur_stream());
+    h2d(r.p, r32_host, 32, cur_stream());
     launch_fold(L, field, W1.p, W2.p, nW, E1.p, T.p, nE, r.p);
-    d2h(W1_host, W1.p, nW * 32, c.stream);
-    d2h(E1_host, E1.p, nE * 32, c.stream);
+    d2h(W1_host, W1.p, nW * 32, cur_stream());
+    d2h(E1_host, E1.p, nE * 32, cur_stream());
     c.launches += L.launches;
-    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    sync_after_unlock(cur_stream());
   });
 }
 
@@ -219,7 +235,7 @@ int vdfgpu_multiply_vec_dev(const vdfgpu_r1cs* s, const void* W_dev, const void*
     if (!s || !uX_dev || !AzBzCz_dev || (s->vars && !W_dev)) throw ArgError("multiply_vec_dev: null pointer");
     require_ready();
     Context& c = ctx();
-    CudaLaunch L(c.stream);
+    CudaLaunch L(cur_stream());
     const fe* ux = reinterpret_cast<const fe*>(uX_dev);
     fe* out = reinterpret_cast<fe*>(AzBzCz_dev);
     launch_multiply_vec(L, s, ZView{reinterpret_cast<const fe*>(W_dev), ux, ux + 1}, out, out + s->cons,
@@ -234,7 +250,7 @@ int vdfgpu_cross_term_dev(const vdfgpu_r1cs* s, const void* W1_dev, const void* 
     if (!s || !uX1_dev || !uX2_dev || !T_dev || (s->vars && (!W1_dev || !W2_dev))) throw ArgError("cross_term_dev: null pointer");
     require_ready();
     Context& c = ctx();
-    CudaLaunch L(c.stream);
+    CudaLaunch L(cur_stream());
     const fe* u1 = reinterpret_cast<const fe*>(uX1_dev);
     const fe* u2 = reinterpret_cast<const fe*>(uX2_dev);
     launch_cross_term(L, s, ZView{reinterpret_cast<const fe*>(W1_dev), u1, u1 + 1},
@@ -250,7 +266,7 @@ int vdfgpu_fold_dev(int field, void* W1_dev, const void* W2_dev, size_t nW, void
     if (!r32_dev || (nW && (!W1_dev || !W2_dev)) || (nE && (!E1_dev || !T_dev))) throw ArgError("fold_dev: null pointer");
     require_ready();
     Context& c = ctx();
-    CudaLaunch L(c.stream);
+    CudaLaunch L(cur_stream());
     launch_fold(L, field, reinterpret_cast<fe*>(W1_dev), reinterpret_cast<const fe*>(W2_dev), nW,
                 reinterpret_cast<fe*>(E1_dev), reinterpret_cast<const fe*>(T_dev), nE, reinterpret_cast<const fe*>(r32_dev));
     c.launches += L.launches;
@@ -283,6 +299,8 @@ int vdfgpu_running_create(const vdfgpu_r1cs* s, vdfgpu_gens* gens, vdfgpu_runnin
       delete f;
       throw;
     }
+    s->refs++;
+    gens->refs++;
     *out = f;
   });
 }
@@ -290,7 +308,12 @@ int vdfgpu_running_create(const vdfgpu_r1cs* s, vdfgpu_gens* gens, vdfgpu_runnin
 int vdfgpu_running_destroy(vdfgpu_running* f) {
   return guarded([&] {
     if (!f) return;
-    if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+    if (ctx().ready) {
+      VDF_CUDA_CHECK(cudaSetDevice(ctx().device));
+      cudaDeviceSynchronize();
+    }
+    f->shape->refs--;
+    f->gens->refs--;
     cudaFree(f->W); cudaFree(f->W2); cudaFree(f->E); cudaFree(f->T); cudaFree(f->uX); cudaFree(f->uX2);
     cudaFree(f->r); cudaFree(f->comm);
     delete f;
@@ -304,11 +327,11 @@ int vdfgpu_running_set(vdfgpu_running* f, const void* W_host, const void* E_host
     if (f->shape->io && !X_host) throw ArgError("running_set: null X");
     require_ready();
     Context& c = ctx();
-    h2d(f->W, W_host, (size_t)f->shape->vars * 32, c.stream);
-    h2d(f->E, E_host, (size_t)f->shape->cons * 32, c.stream);
-    h2d(f->uX, u_host, 32, c.stream);
-    h2d(f->uX + 1, X_host, (size_t)f->shape->io * 32, c.stream);
-    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    h2d(f->W, W_host, (size_t)f->shape->vars * 32, cur_stream());
+    h2d(f->E, E_host, (size_t)f->shape->cons * 32, cur_stream());
+    h2d(f->uX, u_host, 32, cur_stream());
+    h2d(f->uX + 1, X_host, (size_t)f->shape->io * 32, cur_stream());
+    sync_after_unlock(cur_stream());
     f->have_running = true;
     f->have_fresh = false;
   });
@@ -320,38 +343,146 @@ int vdfgpu_running_get(const vdfgpu_running* f, void* W_host, void* E_host, void
     if (!f->have_running) throw StateError("running_get: no running instance set");
     require_ready();
     Context& c = ctx();
-    if (W_host) d2h(W_host, f->W, (size_t)f->shape->vars * 32, c.stream);
-    if (E_host) d2h(E_host, f->E, (size_t)f->shape->cons * 32, c.stream);
-    if (u_host) d2h(u_host, f->uX, 32, c.stream);
-    if (X_host) d2h(X_host, f->uX + 1, (size_t)f->shape->io * 32, c.stream);
-    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    if (W_host) d2h(W_host, f->W, (size_t)f->shape->vars * 32, cur_stream());
+    if (E_host) d2h(E_host, f->E, (size_t)f->shape->cons * 32, cur_stream());
+    if (u_host) d2h(u_host, f->uX, 32, cur_stream());
+    if (X_host) d2h(X_host, f->uX + 1, (size_t)f->shape->io * 32, cur_stream());
+    sync_after_unlock(cur_stream());
   });
 }
 
+// the part of running_commit after W2 / X2 are in place: T, then commit(W2) and commit(T) in one batched pass
+static void running_commit_enqueue(vdfgpu_running* f, void* comm_W2_point96_host, void* comm_T_point96_host) {
+  Context& c = ctx();
+  cudaStream_t st = cur_stream();
+  CudaLaunch L(st);
+  const vdfgpu_r1cs* s = f->shape;
+  launch_cross_term(L, s, ZView{f->W, f->uX, f->uX + 1}, ZView{f->W2, f->uX2, f->uX2 + 1}, f->T);
+  c.launches += L.launches;
+  const fe* vecs[2] = {f->W2, f->T};
+  const size_t lens[2] = {s->vars, s->cons};
+  msm_batch_on_device(f->gens, vecs, lens, 2, f->comm);
+  d2h(comm_W2_point96_host, f->comm, sizeof(jac_t), st);
+  d2h(comm_T_point96_host, f->comm + 1, sizeof(jac_t), st);
+  sync_after_unlock(st);
+  f->have_fresh = true;
+}
+
 int vdfgpu_running_commit(vdfgpu_running* f, const void* W2_host, const void* X2_host, void* comm_W2_point96_host,
-                       void* comm_T_point96_host) {
+                          void* comm_T_point96_host) {
   return guarded([&] {
     if (!f || !W2_host || !comm_W2_point96_host || !comm_T_point96_host) throw ArgError("running_commit: null pointer");
     if (f->shape->io && !X2_host) throw ArgError("running_commit: null X2");
     if (!f->have_running) throw StateError("running_commit: no running instance set");
     require_ready();
-    Context& c = ctx();
-    CudaLaunch L(c.stream);
+    cudaStream_t st = cur_stream();
     const vdfgpu_r1cs* s = f->shape;
     fe one = host_one(s->field);
-    h2d(f->W2, W2_host, (size_t)s->vars * 32, c.stream);
-    h2d(f->uX2, &one, 32, c.stream);
-    h2d(f->uX2 + 1, X2_host, (size_t)s->io * 32, c.stream);
-    // T, then commit(W2) and commit(T) in one batched pass over the shared generators
-    launch_cross_term(L, s, ZView{f->W, f->uX, f->uX + 1}, ZView{f->W2, f->uX2, f->uX2 + 1}, f->T);
-    c.launches += L.launches;
-    const fe* vecs[2] = {f->W2, f->T};
-    const size_t lens[2] = {s->vars, s->cons};
-    msm_batch_on_device(f->gens, vecs, lens, 2, f->comm);
-    d2h(comm_W2_point96_host, f->comm, sizeof(jac_t), c.stream);
-    d2h(comm_T_point96_host, f->comm + 1, sizeof(jac_t), c.stream);
-    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
-    f->have_fresh = true;
+    h2d(f->W2, W2_host, (size_t)s->vars * 32, st);
+    h2d(f->uX2, &one, 32, st);
+    h2d(f->uX2 + 1, X2_host, (size_t)s->io * 32, st);
+    running_commit_enqueue(f, comm_W2_point96_host, comm_T_point96_host);
+  });
+}
+
+// ---- f1: step-circuit witness generation on the device, feeding commit(W) without passing through the host ----
+int vdfgpu_witness_bank_create(int field, const void* z_in_state96_host, uint64_t t, size_t n,
+                               vdfgpu_witness_bank** out) {
+  return guarded([&] {
+    if (!out || !z_in_state96_host) throw ArgError("witness_bank_create: null pointer");
+    if (field != VDFGPU_FP && field != VDFGPU_FQ) throw ArgError("witness_bank_create: unknown field");
+    if (n == 0 || t == 0 || t >= (1ull << 32)) throw ArgError("witness_bank_create: bad dimensions");
+    require_ready();
+    Context& c = ctx();
+    vdfgpu_witness_bank* b = new vdfgpu_witness_bank();
+    b->field = field;
+    b->t = t;
+    b->n = n;
+    const size_t per = 4 * (size_t)t + 1;
+    state_t* d_states = nullptr;
+    try {
+      VDF_CUDA_CHECK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+      VDF_CUDA_CHECK(cudaEventCreateWithFlags(&b->ready, cudaEventDisableTiming));
+      VDF_CUDA_CHECK(cudaMalloc((void**)&b->w, n * per * sizeof(fe)));
+      VDF_CUDA_CHECK(cudaMallocAsync((void**)&d_states, n * sizeof(state_t), b->stream));
+      CudaLaunch L(b->stream);
+      h2d(d_states, z_in_state96_host, n * sizeof(state_t), b->stream);
+      // one thread per step (the rounds of a step are a sequential chain); 32-thread blocks spread few steps
+      // over many SMs.  Runs on the bank's own stream: fold steps of the other curve proceed meanwhile.
+      if (field == VDFGPU_FP) L.run<32>(n, MinRootWitnessFn<Fp>{d_states, t, b->w});
+      else L.run<32>(n, MinRootWitnessFn<Fq>{d_states, t, b->w});
+      VDF_CUDA_CHECK(cudaFreeAsync(d_states, b->stream));
+      VDF_CUDA_CHECK(cudaEventRecord(b->ready, b->stream));
+      c.launches += L.launches;
+      // the caller's state array may be reused after return: wait for the upload only if it was asynchronous
+      // (pinned memory); pageable copies are staged before cudaMemcpyAsync returns
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, z_in_state96_host) == cudaSuccess && at.type == cudaMemoryTypeHost)
+        sync_after_unlock(b->stream);
+      else cudaGetLastError();
+    } catch (...) {
+      if (b->w) cudaFree(b->w);
+      if (b->ready) cudaEventDestroy(b->ready);
+      if (b->stream) cudaStreamDestroy(b->stream);
+      delete b;
+      throw;
+    }
+    *out = b;
+  });
+}
+
+int vdfgpu_witness_bank_destroy(vdfgpu_witness_bank* b) {
+  return guarded([&] {
+    if (!b) return;
+    if (ctx().ready) {
+      VDF_CUDA_CHECK(cudaSetDevice(ctx().device));
+      cudaDeviceSynchronize();
+    }
+    cudaFree(b->w);
+    cudaEventDestroy(b->ready);
+    cudaStreamDestroy(b->stream);
+    delete b;
+  });
+}
+
+int vdfgpu_witness_bank_read(const vdfgpu_witness_bank* b, size_t first_step, size_t count, void* out_fe32_host) {
+  return guarded([&] {
+    if (!b || !out_fe32_host) throw ArgError("witness_bank_read: null pointer");
+    if (first_step + count > b->n) throw ArgError("witness_bank_read: step range out of bounds");
+    require_ready();
+    cudaStream_t st = cur_stream();
+    const size_t per = 4 * (size_t)b->t + 1;
+    VDF_CUDA_CHECK(cudaStreamWaitEvent(st, b->ready, 0));
+    d2h(out_fe32_host, b->w + first_step * per, count * per * sizeof(fe), st);
+    sync_after_unlock(st);
+  });
+}
+
+int vdfgpu_running_commit_step(vdfgpu_running* f, const vdfgpu_witness_bank* bank, size_t step, size_t step_offset,
+                               const void* W2_host, const void* X2_host, void* comm_W2_point96_host,
+                               void* comm_T_point96_host) {
+  return guarded([&] {
+    if (!f || !bank || !comm_W2_point96_host || !comm_T_point96_host) throw ArgError("running_commit_step: null pointer");
+    const vdfgpu_r1cs* s = f->shape;
+    const size_t per = 4 * (size_t)bank->t + 1, nv = s->vars;
+    if (bank->field != s->field) throw ArgError("running_commit_step: the bank's field differs from the R1CS field");
+    if (step >= bank->n) throw ArgError("running_commit_step: step out of range");
+    if (step_offset + per > nv) throw ArgError("running_commit_step: step variables do not fit in W");
+    if (nv > per && !W2_host) throw ArgError("running_commit_step: null W2");
+    if (s->io && !X2_host) throw ArgError("running_commit_step: null X2");
+    if (!f->have_running) throw StateError("running_commit_step: no running instance set");
+    require_ready();
+    cudaStream_t st = cur_stream();
+    fe one = host_one(s->field);
+    const uint8_t* w2 = reinterpret_cast<const uint8_t*>(W2_host);
+    // W2 = [ host part | 4t+1 step variables from the bank | host part ]: the step range never crosses PCIe
+    h2d(f->W2, w2, step_offset * 32, st);
+    h2d(f->W2 + step_offset + per, w2 + (step_offset + per) * 32, (nv - step_offset - per) * 32, st);
+    VDF_CUDA_CHECK(cudaStreamWaitEvent(st, bank->ready, 0));
+    d2d(f->W2 + step_offset, bank->w + step * per, per * 32, st);
+    h2d(f->uX2, &one, 32, st);
+    h2d(f->uX2 + 1, X2_host, (size_t)s->io * 32, st);
+    running_commit_enqueue(f, comm_W2_point96_host, comm_T_point96_host);
   });
 }
 
@@ -361,14 +492,14 @@ int vdfgpu_running_finish(vdfgpu_running* f, const void* r32_host) {
     if (!f->have_fresh) throw StateError("running_finish: fold_commit has not been called for this step");
     require_ready();
     Context& c = ctx();
-    CudaLaunch L(c.stream);
+    CudaLaunch L(cur_stream());
     const vdfgpu_r1cs* s = f->shape;
-    h2d(f->r, r32_host, 32, c.stream);
+    h2d(f->r, r32_host, 32, cur_stream());
     launch_fold(L, s->field, f->W, f->W2, s->vars, f->E, f->T, s->cons, f->r);
     // u <- u + r*1, X <- X + r*X2: the same kernel over the (1 + io)-element tail
     launch_fold(L, s->field, f->uX, f->uX2, 1 + (size_t)s->io, nullptr, nullptr, 0, f->r);
     c.launches += L.launches;
-    VDF_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    sync_after_unlock(cur_stream());
     f->have_fresh = false;
   });
 }

@@ -2,10 +2,13 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
+#include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "../../include/vdfgpu.h"
 #include "launch.cuh"
@@ -20,34 +23,77 @@ struct StateError : std::runtime_error {
   using std::runtime_error::runtime_error;
 };
 
-// one in-flight host-scalar MSM of the asynchronous API (vdfgpu_msm_submit / vdfgpu_msm_wait)
+// Preallocated MSM workspace of one stream (see Arena in launch.cuh).  Grown on demand, never shrunk until
+// vdfgpu_trim() / vdfgpu_shutdown().
+struct Workspace {
+  cudaStream_t stream = nullptr;
+  Arena arena;
+  uint8_t* block = nullptr;
+  size_t block_bytes = 0;
+  uint64_t last_use = 0;
+};
+
+// one in-flight host-scalar MSM of the asynchronous API (vdfgpu_msm_submit / vdfgpu_msm_wait): its own stream
+// carries the upload, the kernels and the read-back, so two slots overlap copies AND kernels
 struct AsyncSlot {
+  cudaStream_t stream = nullptr;
   fe* d_scalars = nullptr;
   size_t cap = 0;
   jac_t* d_out = nullptr;
-  cudaEvent_t copied = nullptr, done = nullptr;
+  cudaEvent_t done = nullptr;
   bool busy = false;
 };
 constexpr int VDF_ASYNC_SLOTS = 4;
 
+// Generator sets kept resident behind the literal pasta-msm entry points mult_pippenger_{pallas,vesta}, which
+// receive the (fixed) points with every call: see api_core.cu "drop-in cache".
+struct DropinEntry {
+  int curve = 0;
+  const void* host_ptr = nullptr;
+  size_t n = 0;
+  std::vector<size_t> sample_idx;       // ascending point indices whose bytes are kept below
+  std::vector<uint8_t> sample_bytes;    // 65 bytes per sampled point (x, y, infinity flag; padding excluded)
+  uint64_t full_hash = 0;               // VDFGPU_DROPIN_VERIFY=full
+  vdfgpu_gens* gens = nullptr;
+  uint64_t last_use = 0;
+};
+
 struct Context {
-  std::mutex mu;          // serialises library calls (re-entrant use from several host threads)
+  std::mutex mu;          // guards this struct while work is ENQUEUED; released before a call blocks on the GPU
   bool ready = false;
   int device = -1;
-  cudaStream_t own_stream = nullptr;
-  cudaStream_t stream = nullptr;  // stream in use (own_stream or the caller's)
+  cudaStream_t own_stream = nullptr;        // library stream: used by every thread that has not set its own
   cudaStream_t copy_stream = nullptr;       // H2D of scalar chunks, overlapped with compute (vdfgpu_msm)
   cudaEvent_t chunk_ev[8] = {};             // chunk k of the scalars has arrived
   cudaEvent_t start_ev = nullptr;
   AsyncSlot slots[VDF_ASYNC_SLOTS];
-  uint64_t launches = 0;
+  std::atomic<uint64_t> launches{0};
   StageProfile prof;      // stage timing of the most recent MSM (vdfgpu_profile_*)
+  std::vector<std::unique_ptr<Workspace>> workspaces;
+  std::vector<DropinEntry> dropin;
+  uint64_t dropin_hits = 0, dropin_misses = 0;
+  uint64_t tick = 0;
 };
 
 Context& ctx();
 void set_error(const std::string& msg);
 void upload_constants_r1cs();   // api_r1cs.cu's copy of the constant-memory tables
-void require_ready();   // throws StateError unless vdfgpu_init succeeded (initialises lazily on device 0)
+void require_ready();           // binds the calling thread to the library's device (lazy vdfgpu_init(0))
+
+// The stream a call enqueues on: the calling THREAD's stream (vdfgpu_set_stream is per thread) or the library's.
+cudaStream_t cur_stream();
+// Ends a blocking entry point: records an event behind the work just enqueued; guarded() waits for it AFTER
+// the context mutex is released, so other threads can enqueue meanwhile.
+void sync_after_unlock(cudaStream_t s);
+void wait_pending_sync();
+struct DeviceScope {   // restores the caller's current device on exit (the library binds its own for the call)
+  int prev = -1;
+  DeviceScope() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+  ~DeviceScope() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
 
 // RAII device buffer on the context stream (stream-ordered)
 template <class T>
@@ -87,12 +133,17 @@ inline void d2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
   if (bytes) VDF_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
 }
 
-// wraps a C-ABI body: locks, maps exceptions to status codes + thread-local message
+// wraps a C-ABI body: locks while the body enqueues, waits for the GPU outside the lock, maps exceptions to
+// status codes + thread-local message, leaves the caller's current device as it found it
 template <class Body>
 int guarded(Body body) {
+  DeviceScope dev;
   try {
-    std::lock_guard<std::mutex> lk(ctx().mu);
-    body();
+    {
+      std::lock_guard<std::mutex> lk(ctx().mu);
+      body();
+    }
+    wait_pending_sync();
     return VDFGPU_OK;
   } catch (const ArgError& e) {
     set_error(e.what());
@@ -116,10 +167,12 @@ struct vdfgpu_gens {
   uint32_t c = 0;          // window bits of the table (table mode)
   uint32_t W = 0;          // levels stored (1 in plain mode)
   vdf::affine_t* pts = nullptr;  // [W][n]
+  int refs = 0;            // running instances holding this set (vdfgpu_gens_destroy refuses while > 0)
 };
 
-// internal cross-TU entry: MSM over device scalars into a device point, on the context stream
+// internal cross-TU entry: MSM over device scalars into a device point, on the calling thread's stream
 namespace vdf {
-void msm_on_device(vdfgpu_gens* g, size_t first, const fe* d_scalars, size_t n, jac_t* d_out, bool is_mont);
+void msm_on_device(vdfgpu_gens* g, size_t first, const fe* d_scalars, size_t n, jac_t* d_out, bool is_mont,
+                   cudaStream_t stream = nullptr);
 void msm_batch_on_device(vdfgpu_gens* g, const fe* const* d_scalars, const size_t* lens, uint32_t k, jac_t* d_out);
 }

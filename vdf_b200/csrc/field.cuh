@@ -154,6 +154,21 @@ struct Field {
     return r;
   }
 
+  // a < m: the canonical range every arithmetic routine here assumes (pasta_curves' from_repr rejects the rest)
+  static VDF_HD bool is_canonical(const fe& a) {
+#if defined(__CUDA_ARCH__)
+    fe t;
+    return sub8_mod(t.v, a.v) != 0;   // a - m borrows
+#else
+    int64_t bw = 0;
+    for (int j = 0; j < 8; j++) {
+      bw += (int64_t)a.v[j] - mod_limb(j);
+      bw >>= 32;
+    }
+    return bw != 0;
+#endif
+  }
+
   static VDF_HD fe neg(const fe& a) { return sub(zero(), a); }
   static VDF_HD fe dbl(const fe& a) { return add(a, a); }
 

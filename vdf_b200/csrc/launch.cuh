@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <stdexcept>
 #include <string>
 
@@ -28,6 +29,93 @@ VDF_HD uint32_t atomic_add_u32(uint32_t* p, uint32_t v) {
   return old;
 #endif
 }
+
+// ---- workspace arena ------------------------------------------------------------------------------
+// Host-side bookkeeping of ONE preallocated device block per stream: the pipelines allocate and free their
+// temporaries here (first fit, lowest address, 256-byte granules) instead of calling cudaMallocAsync /
+// cudaFreeAsync ~30 times per MSM.  All users of one arena run on one stream, so a freed range may be handed
+// out again at once (stream order protects it).  The same allocator run without a device block
+// (PlanLaunch below) replays a pipeline's alloc/free sequence and yields its exact high-water mark, which is
+// how the block is sized before the first launch.  Pointers are stable across calls of the same plan --
+// the precondition for replaying a call as a CUDA graph.
+class Arena {
+ public:
+  static constexpr size_t GRAN = 256;
+  static constexpr size_t UNBOUNDED = (size_t)1 << 60;
+  uint8_t* base = nullptr;   // device block; in measuring mode a fake non-null base that is never dereferenced
+  size_t cap = 0;
+  size_t high = 0;           // high-water mark since reset()
+
+  void reset(size_t capacity) {
+    free_.clear();
+    live_.clear();
+    free_[0] = capacity;
+    cap = capacity;
+    high = 0;
+  }
+  void* alloc(size_t bytes) {
+    const size_t need = (bytes + GRAN - 1) / GRAN * GRAN + GRAN;   // one spare granule: kernels may over-read 16 B
+    for (auto it = free_.begin(); it != free_.end(); ++it) {
+      if (it->second < need) continue;
+      const size_t off = it->first, rest = it->second - need;
+      free_.erase(it);
+      if (rest) free_[off + need] = rest;
+      live_[off] = need;
+      if (off + need > high) high = off + need;
+      return base + off;
+    }
+    throw std::runtime_error("workspace arena exhausted (sizing pass and run disagree)");
+  }
+  void free(void* p) {
+    if (!p) return;
+    const size_t off = (size_t)(reinterpret_cast<uint8_t*>(p) - base);
+    auto lv = live_.find(off);
+    if (lv == live_.end()) throw std::runtime_error("workspace arena: free of an unknown block");
+    size_t size = lv->second, start = off;
+    live_.erase(lv);
+    auto nx = free_.lower_bound(start);
+    if (nx != free_.end() && nx->first == start + size) {   // merge with the block on the right
+      size += nx->second;
+      nx = free_.erase(nx);
+    }
+    if (nx != free_.begin()) {                              // ... and on the left
+      auto pv = std::prev(nx);
+      if (pv->first + pv->second == start) {
+        pv->second += size;
+        return;
+      }
+    }
+    free_[start] = size;
+  }
+
+ private:
+  std::map<size_t, size_t> free_, live_;   // offset -> size
+};
+
+// Sizing pass: the pipeline's host logic with no launches; afterwards arena.high is the workspace it needs.
+struct PlanLaunch {
+  Arena arena;
+  size_t launches = 0;
+  PlanLaunch() {
+    arena.base = reinterpret_cast<uint8_t*>((uintptr_t)1 << 40);
+    arena.reset(Arena::UNBOUNDED);
+  }
+  void mark(int) {}
+  template <class T>
+  T* alloc(size_t count) { return reinterpret_cast<T*>(arena.alloc(count * sizeof(T))); }
+  void free(void* p) { arena.free(p); }
+  void zero(void*, size_t) {}
+  void fill_ff(void*, size_t) {}
+  template <int BLOCK = 256, int MINB = 1, class Fn>
+  void run(size_t n, Fn) { if (n) launches++; }
+  void exclusive_scan(const uint32_t*, uint32_t*, size_t n) {
+    size_t tiles = (n + 2047) / 2048;
+    if (tiles == 0) tiles = 1;
+    uint32_t* t = alloc<uint32_t>(tiles);
+    launches += 3;
+    free(t);
+  }
+};
 
 #if defined(__CUDACC__)
 
@@ -150,8 +238,9 @@ struct CudaLaunch {
   cudaStream_t stream;
   size_t launches = 0;  // kernels launched through this policy (bench.py reports it)
   StageProfile* prof = nullptr;
+  Arena* arena = nullptr;   // preallocated workspace of this stream; nullptr: stream-ordered pool allocations
 
-  explicit CudaLaunch(cudaStream_t s, StageProfile* p = nullptr) : stream(s), prof(p) {}
+  explicit CudaLaunch(cudaStream_t s, StageProfile* p = nullptr, Arena* a = nullptr) : stream(s), prof(p), arena(a) {}
 
   // stage boundary: everything enqueued until the next mark belongs to `stage`
   void mark(int stage) {
@@ -167,12 +256,15 @@ struct CudaLaunch {
 
   template <class T>
   T* alloc(size_t count) {
+    if (arena) return reinterpret_cast<T*>(arena->alloc(count * sizeof(T)));
     void* p = nullptr;
     VDF_CUDA_CHECK(cudaMallocAsync(&p, count * sizeof(T) + 16, stream));
     return reinterpret_cast<T*>(p);
   }
   void free(void* p) {
-    if (p) VDF_CUDA_CHECK(cudaFreeAsync(p, stream));
+    if (!p) return;
+    if (arena) arena->free(p);
+    else VDF_CUDA_CHECK(cudaFreeAsync(p, stream));
   }
   void zero(void* p, size_t bytes) { VDF_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, stream)); }
   void fill_ff(void* p, size_t bytes) { VDF_CUDA_CHECK(cudaMemsetAsync(p, 0xff, bytes, stream)); }

@@ -37,14 +37,21 @@ struct MinRootCheckFn {
     s.x = fe_load(&results[idx].x);
     s.y = fe_load(&results[idx].y);
     s.i = fe_load(&results[idx].i);
-    const fe one = F::one();
-    uint64_t t = t_each ? t_each[idx] : t_uniform;
-#pragma unroll 1
-    for (uint64_t k = 0; k < t; k++) s = minroot_inverse_round<F>(s, one);  // minroot.rs:363-365
     state_t o;
     o.x = fe_load(&originals[idx].x);
     o.y = fe_load(&originals[idx].y);
     o.i = fe_load(&originals[idx].i);
+    // States come from outside: an encoding >= m is not a field element (pasta_curves' from_repr would have
+    // refused it before check() ever ran), so the verdict is "no" rather than arithmetic on an unreduced value
+    if (!(F::is_canonical(s.x) && F::is_canonical(s.y) && F::is_canonical(s.i) && F::is_canonical(o.x) &&
+          F::is_canonical(o.y) && F::is_canonical(o.i))) {
+      ok[idx] = 0;
+      return;
+    }
+    const fe one = F::one();
+    uint64_t t = t_each ? t_each[idx] : t_uniform;
+#pragma unroll 1
+    for (uint64_t k = 0; k < t; k++) s = minroot_inverse_round<F>(s, one);  // minroot.rs:363-365
     ok[idx] = (F::eq(s.x, o.x) && F::eq(s.y, o.y) && F::eq(s.i, o.i)) ? 1 : 0;  // minroot.rs:369-371
   }
 };
