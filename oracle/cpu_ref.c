@@ -71,7 +71,43 @@ static inline void fe_sub(fe* r, const fe* a, const fe* b, const field_t* f) {
 
 static inline void fe_neg(fe* r, const fe* a, const field_t* f) { fe z = {{0, 0, 0, 0}}; fe_sub(r, &z, a, f); }
 
-/* CIOS Montgomery multiplication, 4 x 64-bit limbs */
+/* Montgomery multiplication, 4 x 64-bit limbs, R = 2^256 (pasta_curves' representation).
+ *
+ * x86-64 with BMI2 + ADX: CIOS with the two carry chains of MULX / ADCX / ADOX, the scheme of the assembly that
+ * pasta-msm's field layer (semolina) and blst use; valid because the top limb of both moduli is 2^62 (no carry out
+ * of the fifth limb).  Measured on the build host against the portable u128 loop below: see DESIGN.md section 6.
+ * Other targets: the portable CIOS loop. */
+#if defined(__x86_64__) && defined(__BMI2__) && defined(__ADX__) && !defined(VDF_REF_PORTABLE)
+#define VDF_REF_ADX 1
+#define MONT_ROW(boff)                                                                          \
+  "movq " #boff "(%[b]), %%rdx\n\t"                                                             \
+  "xorq %[lo], %[lo]\n\t"                                                                       \
+  "mulx 0(%[a]), %[lo], %[hi]\n\t"  "adox %[lo], %[t0]\n\t"                                     \
+  "adcx %[hi], %[t1]\n\t" "mulx 8(%[a]), %[lo], %[hi]\n\t"  "adox %[lo], %[t1]\n\t"             \
+  "adcx %[hi], %[t2]\n\t" "mulx 16(%[a]), %[lo], %[hi]\n\t" "adox %[lo], %[t2]\n\t"             \
+  "adcx %[hi], %[t3]\n\t" "mulx 24(%[a]), %[lo], %[A]\n\t"  "adox %[lo], %[t3]\n\t"             \
+  "movl $0, %k[lo]\n\t"   "adcx %[lo], %[A]\n\t"            "adox %[lo], %[A]\n\t"              \
+  "movq %[inv], %%rdx\n\t" "imulq %[t0], %%rdx\n\t"                                             \
+  "xorq %[lo], %[lo]\n\t"                                                                       \
+  "mulx 0(%[m]), %[lo], %[hi]\n\t"  "adcx %[t0], %[lo]\n\t" "movq %[hi], %[t0]\n\t"             \
+  "adcx %[t1], %[t0]\n\t" "mulx 8(%[m]), %[lo], %[t1]\n\t"  "adox %[lo], %[t0]\n\t"             \
+  "adcx %[t2], %[t1]\n\t" "mulx 16(%[m]), %[lo], %[t2]\n\t" "adox %[lo], %[t1]\n\t"             \
+  "adcx %[t3], %[t2]\n\t" "mulx 24(%[m]), %[lo], %[t3]\n\t" "adox %[lo], %[t2]\n\t"             \
+  "movl $0, %k[lo]\n\t"   "adcx %[lo], %[t3]\n\t"           "adox %[A], %[t3]\n\t"
+
+static inline void fe_mul(fe* r, const fe* a, const fe* b, const field_t* f) {
+  uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, A, lo, hi;
+  __asm__(MONT_ROW(0) MONT_ROW(8) MONT_ROW(16) MONT_ROW(24)
+          : [t0] "+&r"(t0), [t1] "+&r"(t1), [t2] "+&r"(t2), [t3] "+&r"(t3), [A] "=&r"(A), [lo] "=&r"(lo), [hi] "=&r"(hi)
+          : [a] "r"(a->l), [b] "r"(b->l), [m] "r"(f->m.l), [inv] "rm"(f->inv), "m"(*a), "m"(*b), "m"(f->m)
+          : "rdx", "cc");
+  fe o = {{t0, t1, t2, t3}};
+  fe_cond_sub(&o, 0, f);
+  *r = o;
+}
+static inline void fe_sqr(fe* r, const fe* a, const field_t* f) { fe_mul(r, a, a, f); }
+#else
+/* portable CIOS, u128 accumulators */
 static inline void fe_mul(fe* r, const fe* a, const fe* b, const field_t* f) {
   uint64_t t[6] = {0, 0, 0, 0, 0, 0};
   for (int i = 0; i < 4; i++) {
@@ -88,6 +124,7 @@ static inline void fe_mul(fe* r, const fe* a, const fe* b, const field_t* f) {
   *r = o;
 }
 static inline void fe_sqr(fe* r, const fe* a, const field_t* f) { fe_mul(r, a, a, f); }
+#endif
 
 static void fe_from_mont(fe* r, const fe* a, const field_t* f) { fe one = {{1, 0, 0, 0}}; fe_mul(r, a, &one, f); }
 
@@ -167,28 +204,68 @@ static const field_t* base_field(int curve) { return curve == 0 ? &FP : &FQ; }
 static const field_t* scalar_field(int curve) { return curve == 0 ? &FQ : &FP; }
 static const field_t* field_by_id(int id) { return id == 0 ? &FP : &FQ; }
 
-/* ---- thread pool-ish helper: run fn(task) for task in [0, ntasks) on nthreads ---- */
-typedef struct { void (*fn)(void*, size_t); void* arg; size_t ntasks; size_t next; pthread_mutex_t mu; } pool_t;
-static void* pool_worker(void* p_) {
-  pool_t* p = (pool_t*)p_;
+/* ---- persistent thread pool: run fn(arg, task) for task in [0, ntasks) on up to nthreads threads -------------
+ * Workers are created once and sleep on a condition variable between jobs (pasta-msm / sppark keep a thread pool
+ * too); the calling thread works alongside them.  One job at a time (callers are serialised by job_mu). */
+#define POOL_MAX 256
+static struct {
+  pthread_mutex_t job_mu, mu;
+  pthread_cond_t wake, done;
+  pthread_t th[POOL_MAX];
+  int nworkers;
+  unsigned long generation;
+  void (*fn)(void*, size_t);
+  void* arg;
+  size_t ntasks, next, finished;
+  int active_limit, active;      /* workers allowed to join this job / workers that did */
+} g_pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER,
+            {0}, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+
+static void pool_drain(void) {   /* called with g_pool.mu held; returns with it held */
+  while (g_pool.next < g_pool.ntasks) {
+    size_t t = g_pool.next++;
+    pthread_mutex_unlock(&g_pool.mu);
+    g_pool.fn(g_pool.arg, t);
+    pthread_mutex_lock(&g_pool.mu);
+    if (++g_pool.finished == g_pool.ntasks) pthread_cond_broadcast(&g_pool.done);
+  }
+}
+
+static void* pool_worker(void* unused) {
+  (void)unused;
+  unsigned long seen = 0;
+  pthread_mutex_lock(&g_pool.mu);
   for (;;) {
-    pthread_mutex_lock(&p->mu);
-    size_t t = p->next++;
-    pthread_mutex_unlock(&p->mu);
-    if (t >= p->ntasks) break;
-    p->fn(p->arg, t);
+    while (g_pool.generation == seen) pthread_cond_wait(&g_pool.wake, &g_pool.mu);
+    seen = g_pool.generation;
+    if (g_pool.active < g_pool.active_limit) {
+      g_pool.active++;
+      pool_drain();
+    }
   }
   return NULL;
 }
+
 static void parallel_for(size_t ntasks, int nthreads, void (*fn)(void*, size_t), void* arg) {
-  pool_t p = {fn, arg, ntasks, 0, PTHREAD_MUTEX_INITIALIZER};
   if (nthreads < 1) nthreads = 1;
+  if (nthreads > POOL_MAX) nthreads = POOL_MAX;
   if ((size_t)nthreads > ntasks) nthreads = (int)ntasks;
   if (nthreads <= 1) { for (size_t t = 0; t < ntasks; t++) fn(arg, t); return; }
-  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
-  for (int i = 0; i < nthreads; i++) pthread_create(&th[i], NULL, pool_worker, &p);
-  for (int i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
-  free(th);
+  pthread_mutex_lock(&g_pool.job_mu);
+  pthread_mutex_lock(&g_pool.mu);
+  while (g_pool.nworkers < nthreads - 1) {
+    if (pthread_create(&g_pool.th[g_pool.nworkers], NULL, pool_worker, NULL) != 0) break;
+    pthread_detach(g_pool.th[g_pool.nworkers]);
+    g_pool.nworkers++;
+  }
+  g_pool.fn = fn; g_pool.arg = arg; g_pool.ntasks = ntasks; g_pool.next = 0; g_pool.finished = 0;
+  g_pool.active_limit = nthreads - 1; g_pool.active = 0;
+  g_pool.generation++;
+  pthread_cond_broadcast(&g_pool.wake);
+  pool_drain();
+  while (g_pool.finished < g_pool.ntasks) pthread_cond_wait(&g_pool.done, &g_pool.mu);
+  pthread_mutex_unlock(&g_pool.mu);
+  pthread_mutex_unlock(&g_pool.job_mu);
 }
 
 /* ---- MSM ---- */
@@ -282,27 +359,69 @@ int ref_msm(int curve, const uint8_t* affine72, size_t n, const uint8_t* scalars
   return 0;
 }
 
-/* known-dlog progression P_i = (k0 + i d) G, G = (-1, 2): synthetic generator sets for the CPU baseline */
-int ref_progression(int curve, const uint8_t* k0_le32, const uint8_t* d_le32, size_t n, uint8_t* out72) {
+/* known-dlog progression P_i = (k0 + i d) G, G = (-1, 2): synthetic generator sets for the CPU baseline.
+ * Point ranges run in parallel (range start = K0 + lo * D by double-and-add over the 64-bit lo), each range is
+ * normalised to affine with batched inversions (Montgomery's trick, 256 points per inversion). */
+typedef struct { const field_t* f; xyzz_t K0, D; fe dx, dy; int d_inf; size_t n, chunk; uint8_t* out72; } prog_job_t;
+
+static void prog_task(void* arg, size_t task) {
+  prog_job_t* j = (prog_job_t*)arg;
+  const field_t* f = j->f;
+  size_t lo = task * j->chunk, hi = lo + j->chunk < j->n ? lo + j->chunk : j->n;
+  xyzz_t cur; memset(&cur, 0, sizeof cur);
+  for (int bit = 63; bit >= 0; bit--) {               /* cur = lo * D */
+    xyzz_t t = cur; xyzz_dbl(&cur, &t, f);
+    if (((uint64_t)lo >> bit) & 1) xyzz_add(&cur, &j->D, f);
+  }
+  xyzz_add(&cur, &j->K0, f);
+  enum { B = 256 };
+  xyzz_t q[B]; fe pre[B];
+  for (size_t base = lo; base < hi; base += B) {
+    size_t m = base + B < hi ? B : hi - base;
+    fe run = f->one;
+    for (size_t k = 0; k < m; k++) {
+      q[k] = cur; pre[k] = run;
+      if (!xyzz_is_inf(&cur)) { fe t; fe_mul(&t, &cur.ZZ, &cur.ZZZ, f); fe_mul(&run, &run, &t, f); }
+      if (!j->d_inf) xyzz_madd(&cur, &j->dx, &j->dy, f);
+    }
+    fe inv; fe_inv(&inv, &run, f);
+    for (size_t k = m; k-- > 0;) {
+      uint8_t* o = j->out72 + 72 * (base + k);
+      memset(o, 0, 72);
+      if (xyzz_is_inf(&q[k])) { o[64] = 1; continue; }
+      fe zi, t, x, y;
+      fe_mul(&zi, &inv, &pre[k], f);                                  /* 1 / (ZZ * ZZZ) */
+      fe_mul(&t, &q[k].ZZ, &q[k].ZZZ, f); fe_mul(&inv, &inv, &t, f);
+      fe_mul(&t, &zi, &q[k].ZZZ, f); fe_mul(&x, &q[k].X, &t, f);
+      fe_mul(&t, &zi, &q[k].ZZ, f); fe_mul(&y, &q[k].Y, &t, f);
+      memcpy(o, &x, 32); memcpy(o + 32, &y, 32);
+    }
+  }
+}
+
+int ref_progression_mt(int curve, const uint8_t* k0_le32, const uint8_t* d_le32, size_t n, int nthreads, uint8_t* out72) {
   const field_t* f = base_field(curve);
   fe gx, gy; fe_neg(&gx, &f->one, f); fe_add(&gy, &f->one, &f->one, f);
   fe k0, d; memcpy(&k0, k0_le32, 32); memcpy(&d, d_le32, 32);
-  xyzz_t cur, D; memset(&cur, 0, sizeof cur); memset(&D, 0, sizeof D);
+  prog_job_t j; j.f = f; j.n = n; j.out72 = out72;
+  memset(&j.K0, 0, sizeof j.K0); memset(&j.D, 0, sizeof j.D);
   for (int i = 255; i >= 0; i--) {
-    xyzz_t t = cur; xyzz_dbl(&cur, &t, f); t = D; xyzz_dbl(&D, &t, f);
-    if ((k0.l[i >> 6] >> (i & 63)) & 1) xyzz_madd(&cur, &gx, &gy, f);
-    if ((d.l[i >> 6] >> (i & 63)) & 1) xyzz_madd(&D, &gx, &gy, f);
+    xyzz_t t = j.K0; xyzz_dbl(&j.K0, &t, f); t = j.D; xyzz_dbl(&j.D, &t, f);
+    if ((k0.l[i >> 6] >> (i & 63)) & 1) xyzz_madd(&j.K0, &gx, &gy, f);
+    if ((d.l[i >> 6] >> (i & 63)) & 1) xyzz_madd(&j.D, &gx, &gy, f);
   }
-  uint8_t dj[96]; xyzz_to_jac96(dj, &D, f);
-  fe dx, dy; memcpy(&dx, dj, 32); memcpy(&dy, dj + 32, 32);
-  int d_inf = xyzz_is_inf(&D);
-  for (size_t i = 0; i < n; i++) {
-    uint8_t pj[96]; xyzz_to_jac96(pj, &cur, f);   /* one inversion per point: fine for baseline-size inputs */
-    memset(out72 + 72 * i, 0, 72);
-    if (xyzz_is_inf(&cur)) out72[72 * i + 64] = 1; else memcpy(out72 + 72 * i, pj, 64);
-    if (!d_inf) xyzz_madd(&cur, &dx, &dy, f);
-  }
+  uint8_t dj[96]; xyzz_to_jac96(dj, &j.D, f);
+  memcpy(&j.dx, dj, 32); memcpy(&j.dy, dj + 32, 32);
+  j.d_inf = xyzz_is_inf(&j.D);
+  if (nthreads < 1) nthreads = 1;
+  j.chunk = (n + (size_t)nthreads * 4 - 1) / ((size_t)nthreads * 4);
+  if (j.chunk < 256) j.chunk = 256;
+  if (n) parallel_for((n + j.chunk - 1) / j.chunk, nthreads, prog_task, &j);
   return 0;
+}
+
+int ref_progression(int curve, const uint8_t* k0_le32, const uint8_t* d_le32, size_t n, uint8_t* out72) {
+  return ref_progression_mt(curve, k0_le32, d_le32, n, 1, out72);
 }
 
 /* ---- MinRoot check (src/minroot.rs:338-371) ---- */

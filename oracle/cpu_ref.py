@@ -13,9 +13,33 @@ _LIB = _DIR / "libvdf_cpu_ref.so"
 _lib = None
 
 
+def _host_signature() -> str:
+    """CPU model + ISA flags of this machine: the library is compiled with -march=native, so a copy built on another
+    host (the build container vs the GPU box) is rebuilt before it is loaded."""
+    import hashlib
+    model, flags = "", ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name") and not model:
+                model = line.split(":", 1)[1].strip()
+            elif line.startswith("flags") and not flags:
+                flags = line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return model + " " + hashlib.sha1(flags.encode()).hexdigest()[:12]
+
+
 def build() -> Path:
-    if not _LIB.exists() or _LIB.stat().st_mtime < (_DIR / "cpu_ref.c").stat().st_mtime:
-        subprocess.run(["make", "-s", "-C", str(_DIR)], check=True)
+    sig_file = _DIR / "libvdf_cpu_ref.host"
+    sig = _host_signature()
+    stale = (not _LIB.exists() or _LIB.stat().st_mtime < (_DIR / "cpu_ref.c").stat().st_mtime
+             or not sig_file.exists() or sig_file.read_text() != sig)
+    if stale:
+        try:
+            subprocess.run(["make", "-s", "-B", "-C", str(_DIR)], check=True)
+        except (subprocess.CalledProcessError, OSError):
+            subprocess.run(["make", "-s", "-B", "-C", str(_DIR), "ARCH=x86-64-v3"], check=True)
+        sig_file.write_text(sig)
     return _LIB
 
 
@@ -53,9 +77,10 @@ def msm(curve: int, affine72: bytes, scalars: bytes, is_mont: bool = True, nthre
     return bytes(out)
 
 
-def progression(curve: int, k0: int, d: int, n: int) -> bytes:
+def progression(curve: int, k0: int, d: int, n: int, nthreads: int = 0) -> bytes:
     out = bytearray(72 * n)
-    load().ref_progression(c_int(curve), _p(k0.to_bytes(32, "little")), _p(d.to_bytes(32, "little")), c_size_t(n), _p(out))
+    load().ref_progression_mt(c_int(curve), _p(k0.to_bytes(32, "little")), _p(d.to_bytes(32, "little")), c_size_t(n),
+                              c_int(nthreads or ncores()), _p(out))
     return bytes(out)
 
 

@@ -167,3 +167,13 @@ def test_package_synthetic_generator_matches_oracle_semantics():
         vdf = O.MinRootVDF(fid)
         s = vdf.inverse_eval(O.State(W[-4 * 12 - 4], W[-4 * 12 - 3], W[-4 * 12 - 2]), 12)
         assert (W[-5], W[-2], W[-1]) == (s.x, s.y, s.i)      # last round's new_x, new_y and final_i
+
+
+def test_known_dlog_numpy_helper():
+    """tests/util.known_dlog_scalar (the O(n) numpy side of the 2^24 / 2^26 GPU parity tests) against Python ints."""
+    import numpy as np
+    from tests.util import known_dlog_scalar
+    rs = np.random.RandomState(1)
+    raw = rs.randint(0, 1 << 32, size=(40000, 8), dtype=np.uint64).astype(np.uint32)
+    want = sum(int.from_bytes(raw[i].tobytes(), "little") * (7 + (5 + i) * 11) for i in range(raw.shape[0]))
+    assert known_dlog_scalar(raw, 7, 11, first=5) == want

@@ -40,3 +40,6 @@ def nova_like_scalars(pyrng: random.Random, rng: O.XorShiftRng, m: int, n: int):
 def edge_field_values(m: int):
     return [0, 1, 2, m - 1, m - 2, (1 << 254), (1 << 254) - 1, (1 << 128), (1 << 128) - 1, 0xFFFFFFFF, 1 << 32,
             (m - 1) // 2, (m + 1) // 2]
+
+
+from vdf_b200.encoding import known_dlog_scalar  # noqa: E402,F401  (O(n) numpy side of the known-dlog identity)

@@ -72,3 +72,29 @@ def point_from_bytes(b: bytes, base: int) -> Affine:
         return None
     zi = pow(Z, -1, base)
     return (X * zi * zi % base, Y * zi * zi * zi % base)
+
+
+def known_dlog_scalar(raw, k0: int, d: int, first: int = 0) -> int:
+    """sum_i s_i * (k0 + (first + i) d) over the 256-bit little-endian integers s_i = raw[i, 0..7] (u32 limbs),
+    in O(n) numpy work: 2^15-element chunks keep every partial sum below 2^63."""
+    import numpy as np
+    n = raw.shape[0]
+    CH = 1 << 15
+    pad = (-n) % CH
+    j = np.arange(CH, dtype=np.uint64)
+    s_tot = s_idx = 0
+    for limb in range(8):
+        col = raw[:, limb].astype(np.uint64)
+        if pad:
+            col = np.concatenate([col, np.zeros(pad, dtype=np.uint64)])
+        A = col.reshape(-1, CH)
+        csum = A.sum(axis=1)                      # < 2^47 each
+        cjsum = (A * j).sum(axis=1)               # < 2^62 each
+        tot = idx = 0
+        for c in range(A.shape[0]):
+            cs = int(csum[c])
+            tot += cs
+            idx += (first + c * CH) * cs + int(cjsum[c])
+        s_tot += tot << (32 * limb)
+        s_idx += idx << (32 * limb)
+    return k0 * s_tot + d * s_idx

@@ -107,6 +107,38 @@ def challenge(*chunks: bytes) -> int:
     return int.from_bytes(h.digest(), "little")
 
 
+class WitnessBank:
+    """Step-circuit witnesses (4t+1 values per step, src/nova/proof.rs:107-126, :162-189) of all steps of a proof,
+    generated and kept on the device.  `states` are the steps' input states (x, y, i)."""
+
+    def __init__(self, field_id: int, states: Sequence[Tuple[int, int, int]], t: int):
+        m = MODULUS[field_id]
+        self.field_id, self.t, self.n, self.m = field_id, t, len(states), m
+        raw = b"".join(fes_to_bytes(list(s), m) for s in states)
+        h = ctypes.c_void_p()
+        _lib.check(_lib.load().vdfgpu_witness_bank_create(field_id, _lib.as_ptr(raw), t, len(states), ctypes.byref(h)))
+        self._h = h
+
+    def read(self, first: int = 0, count: Optional[int] = None) -> List[List[int]]:
+        count = self.n - first if count is None else count
+        per = 4 * self.t + 1
+        buf = bytearray(count * per * 32)
+        _lib.check(_lib.load().vdfgpu_witness_bank_read(self._h, first, count, _lib.as_ptr(buf)))
+        flat = fes_from_bytes(bytes(buf), self.m)
+        return [flat[k * per:(k + 1) * per] for k in range(count)]
+
+    def close(self):
+        if self._h:
+            _lib.load().vdfgpu_witness_bank_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 @dataclass
 class RelaxedR1CSInstance:  # nova RelaxedR1CSInstance
     comm_W: Affine
@@ -153,6 +185,16 @@ class RunningProver:
             # the transcript absorbs canonical (affine) encodings, as nova's RO does via to_affine()
             base = CURVE_BASE[self.gens.curve]
             r = challenge(*[affine_to_bytes(point_from_bytes(bytes(c), base), base) for c in (cW, cT)])
+        _lib.check(lib.vdfgpu_running_finish(self._h, _lib.as_ptr(fe_to_bytes(r, self.shape.m))))
+        return bytes(cW), bytes(cT), r
+
+    def prove_step_bank_bytes(self, bank: WitnessBank, step: int, step_offset: int, W2: bytes, X2: bytes, r: int):
+        """prove_step_bytes with the 4t+1 step variables of W2 taken from the device-resident bank: the bytes of
+        W2[step_offset : step_offset + 4t + 1] are ignored and never transferred."""
+        lib = _lib.load()
+        cW, cT = bytearray(POINT_BYTES), bytearray(POINT_BYTES)
+        _lib.check(lib.vdfgpu_running_commit_step(self._h, bank._h, step, step_offset, _lib.as_ptr(W2), _lib.as_ptr(X2),
+                                                  _lib.as_ptr(cW), _lib.as_ptr(cT)))
         _lib.check(lib.vdfgpu_running_finish(self._h, _lib.as_ptr(fe_to_bytes(r, self.shape.m))))
         return bytes(cW), bytes(cT), r
 
