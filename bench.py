@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=22, help="points per GPU = 2^log2n")
     ap.add_argument("--plain", action="store_true", help="plain generator layout instead of the table")
-    ap.add_argument("--inflight", type=int, default=2, choices=[1, 2], help="independent commitments in flight in the device-timed region")
+    ap.add_argument("--inflight", type=int, default=4, choices=[1, 2, 3, 4], help="independent commitments in flight in the device-timed region and in the pipelined e2e")
     ap.add_argument("--no-extra", action="store_true", help="skip every side measurement")
     ap.add_argument("--no-sweep", action="store_true", help="skip the 2^20..2^26 size sweep / strong-scaling leg")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="wall-time budget of the CPU reference arm")
@@ -484,8 +484,8 @@ class MsmRunner:
         gen = torch.Generator(device="cuda")
         gen.manual_seed(seed)
         self.scal = rand_fe_dev(torch, n, gen)
-        self.outs = [torch.zeros(96, dtype=torch.uint8, device="cuda") for _ in range(2)]
-        self.streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        self.outs = [torch.zeros(96, dtype=torch.uint8, device="cuda") for _ in range(4)]
+        self.streams = [torch.cuda.Stream() for _ in range(4)]
 
     def launch(self, slot):
         """enqueue one commitment on stream `slot` (each stream has its own workspace arena inside the library)"""
@@ -499,24 +499,27 @@ class MsmRunner:
         behind every commitment on its stream (the multi-GPU combine)"""
         torch = self.torch
         ctx_stream = torch.cuda.current_stream()
-        A, B = self.streams
+        A, others = self.streams[0], self.streams[1:inflight]
 
         def run(count):
             for k in range(count):
-                slot = k & 1 if inflight == 2 else 0
+                slot = k % inflight
                 s = self.launch(slot)
                 if after:
                     with torch.cuda.stream(s):
                         after(slot, s)
 
-        run(warm)
+        run(max(warm, inflight) if warm else 0)     # every stream's workspace exists before the timed region
         torch.cuda.synchronize()
-        e0, e1, eb = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(A)
-        B.wait_event(e0)
+        for s in others:
+            s.wait_event(e0)
         run(steps)
-        eb.record(B)
-        A.wait_event(eb)
+        for s in others:
+            ev = torch.cuda.Event()
+            ev.record(s)
+            A.wait_event(ev)
         e1.record(A)
         torch.cuda.synchronize()
         self._lib.check(self.lib.vdfgpu_set_stream(ctx_stream.cuda_stream))
@@ -536,10 +539,10 @@ def sweep_measurements(lib, _lib, torch, log2s=(20, 22, 24, 26)):
             r = MsmRunner(torch, lib, _lib, n)
             reps = 6 if lg <= 22 else (4 if lg == 24 else 3)
             ser = r.timed(reps, 1)
-            try:
-                two = r.timed(reps, 2)
-            except Exception:
-                two = None     # a second workspace may not fit beside the 2^26 table
+            deep = None
+            if lg <= 24:       # several workspaces do not fit beside the 55 GB table of 2^26 points
+                deep = r.timed(max(reps, 8), 4)
+            _lib.check(lib.vdfgpu_trim())
             host = torch.empty((n, 4), dtype=torch.int64, pin_memory=True)
             host.copy_(r.scal)
             out_h = torch.zeros(96, dtype=torch.uint8, pin_memory=True)
@@ -550,7 +553,7 @@ def sweep_measurements(lib, _lib, torch, log2s=(20, 22, 24, 26)):
             e2e = (time.perf_counter() - t0) / reps
             out[str(lg)] = {"n": n, "window_bits": r.gens.window_bits(n), "affine_rounds": r.gens.affine_rounds(n),
                             "serial_ms": ser, "serial_gpoints_s": n / ser / 1e6,
-                            "inflight2_ms": two, "inflight2_gpoints_s": (n / two / 1e6) if two else None,
+                            "inflight4_ms": deep, "inflight4_gpoints_s": (n / deep / 1e6) if deep else None,
                             "sync_e2e_pinned_ms": e2e * 1e3, "sync_e2e_pinned_gpoints_s": n / e2e / 1e9,
                             "gens_setup_ms": r.setup_s * 1e3}
             r.close()
@@ -623,23 +626,24 @@ def strong_scaling(torch, dist, lib, _lib, rank, world, totals=(24, 26)):
                 torch.cuda.empty_cache()
             dist.barrier()
             r = MsmRunner(torch, lib, _lib, n, k0=K0 + rank * n * D, raw=True, seed=1000 + rank)
-            gathered = [torch.zeros(96 * world, dtype=torch.uint8, device="cuda") for _ in range(2)]
-            total_dev = [torch.zeros(96, dtype=torch.uint8, device="cuda") for _ in range(2)]
+            gathered = [torch.zeros(96 * world, dtype=torch.uint8, device="cuda") for _ in range(4)]
+            total_dev = [torch.zeros(96, dtype=torch.uint8, device="cuda") for _ in range(4)]
 
-            def combine(k, s):
-                dist.all_gather_into_tensor(gathered[k & 1], r.outs[k & 1])
+            def combine(slot, s):
+                dist.all_gather_into_tensor(gathered[slot], r.outs[slot])
                 _lib.check(lib.vdfgpu_set_stream(s.cuda_stream))
-                _lib.check(lib.vdfgpu_point_sum_dev(0, gathered[k & 1].data_ptr(), world, total_dev[k & 1].data_ptr()))
+                _lib.check(lib.vdfgpu_point_sum_dev(0, gathered[slot].data_ptr(), world, total_dev[slot].data_ptr()))
 
             res = {}
-            for inflight in (1, 2):
+            deep = 4 if n <= (1 << 24) else 2
+            for inflight in (1, deep):
                 dist.barrier()
-                ms = r.timed(5, inflight, after=combine)
+                ms = r.timed(6 if inflight == 1 else 8, inflight, after=combine)
                 t = torch.tensor([ms], dtype=torch.float64, device="cuda")
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 res[inflight] = float(t.item())
             entry.update({"serial_ms": res[1], "serial_gpoints_s": total / res[1] / 1e6,
-                          "inflight2_ms": res[2], "inflight2_gpoints_s": total / res[2] / 1e6})
+                          "inflight": deep, "inflight_ms": res[deep], "inflight_gpoints_s": total / res[deep] / 1e6})
             if rank == 0:
                 entry["single_gpu_serial_ms"] = single
                 entry["speedup_vs_single_gpu_serial"] = single / res[1]
@@ -684,7 +688,7 @@ def run_ours(args):
 
     n = 1 << args.log2n
     table = not args.plain
-    steps, warmup = args.steps, max(3, args.warmup)
+    steps, warmup = args.steps, max(3, args.warmup, args.inflight)   # every in-flight slot is warmed up at least once
 
     # generators: this rank's contiguous point range of the global progression; with several GPUs the partial results
     # stay un-normalised (one inversion after the combine instead of one per rank plus one)
@@ -694,13 +698,13 @@ def run_ours(args):
     W = (256 + c_bits - 1) // c_bits
     scal_host = torch.empty((n, 4), dtype=torch.int64, pin_memory=True)
     scal_host.copy_(scal)
-    gathered = [torch.zeros(96 * world, dtype=torch.uint8, device="cuda") for _ in range(2)] if world > 1 else None
-    total_dev = [torch.zeros(96, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    gathered = [torch.zeros(96 * world, dtype=torch.uint8, device="cuda") for _ in range(4)] if world > 1 else None
+    total_dev = [torch.zeros(96, dtype=torch.uint8, device="cuda") for _ in range(4)]
 
-    def combine(k, s):
-        dist.all_gather_into_tensor(gathered[k & 1], runner.outs[k & 1])
+    def combine(slot, s):
+        dist.all_gather_into_tensor(gathered[slot], runner.outs[slot])
         _lib.check(lib.vdfgpu_set_stream(s.cuda_stream))
-        _lib.check(lib.vdfgpu_point_sum_dev(0, gathered[k & 1].data_ptr(), world, total_dev[k & 1].data_ptr()))
+        _lib.check(lib.vdfgpu_point_sum_dev(0, gathered[slot].data_ptr(), world, total_dev[slot].data_ptr()))
 
     after = combine if world > 1 else None
 
@@ -729,10 +733,8 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     value = world * n / (ms_per_step * 1e-3) / 1e9
     barrier()
-    other = 1 if args.inflight == 2 else 2
-    other_ms = max_over_ranks(runner.timed(steps, other, warm=1, after=after))
-    serial_ms = other_ms if other == 1 else ms_per_step
-    inflight2_ms = ms_per_step if args.inflight == 2 else other_ms
+    # the same K commitments one at a time on one stream (runs last: slot 0 then holds the final result)
+    serial_ms = ms_per_step if args.inflight == 1 else max_over_ranks(runner.timed(steps, 1, warm=1, after=after))
     _lib.check(lib.vdfgpu_set_stream(stream.cuda_stream))
 
     # ---- parity of the (combined) commitment: known-discrete-log identity, every rank ----
@@ -780,11 +782,12 @@ def run_ours(args):
     pageable = scal_host.numpy().copy()                       # ordinary malloc'ed memory, what a Rust Vec is
     e2e_sync(pageable.ctypes.data, 1)
     sync_pageable_s = e2e_sync(pageable.ctypes.data, max(3, steps // 2))
-    # the asynchronous form of the same call, two commitments in flight: every step still uploads its own n*32 bytes
-    # from pinned host memory and reads its own 96-byte result back, but upload and latency-bound stages of step k+1
-    # run under the kernels of step k.  Independent commitments (the microbenchmark's case) allow this; the serial
-    # MSMs of one Nova step do not, which is why all three numbers are reported.
-    outs = [torch.zeros(96, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    # the asynchronous form of the same call, `depth` commitments in flight: every step still uploads its own n*32
+    # bytes from pinned host memory and reads its own 96-byte result back, but the upload and the latency-bound stages
+    # of one step run under the kernels of the others.  Independent commitments (the microbenchmark's case) allow
+    # this; the serial MSMs of one Nova step do not, which is why all three numbers are reported.
+    depth = max(2, args.inflight)
+    outs = [torch.zeros(96, dtype=torch.uint8, pin_memory=True) for _ in range(depth)]
 
     def finish(slot):
         _lib.check(lib.vdfgpu_msm_wait(slot))
@@ -792,13 +795,14 @@ def run_ours(args):
             combine_host(outs[slot])
 
     def pipelined(k_steps):
-        _lib.check(lib.vdfgpu_msm_submit(gens._h, scal_host.data_ptr(), n, outs[0].data_ptr(), 0))
-        for k in range(1, k_steps):
-            _lib.check(lib.vdfgpu_msm_submit(gens._h, scal_host.data_ptr(), n, outs[k & 1].data_ptr(), k & 1))
-            finish((k - 1) & 1)
-        finish((k_steps - 1) & 1)
+        for k in range(k_steps):
+            if k >= depth:
+                finish(k % depth)
+            _lib.check(lib.vdfgpu_msm_submit(gens._h, scal_host.data_ptr(), n, outs[k % depth].data_ptr(), k % depth))
+        for k in range(max(0, k_steps - depth), k_steps):
+            finish(k % depth)
 
-    pipelined(2)
+    pipelined(2 * depth)
     barrier()
     t0 = time.perf_counter()
     pipelined(steps)
@@ -808,7 +812,7 @@ def run_ours(args):
         raise SystemExit("bench.py: pipelined and synchronous commitments differ")
     e2e = {"value": world * n / e2e_s / 1e9, "unit": "Gpoints/s", "ms_per_step": e2e_s * 1e3,
            "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 96,
-           "api": "vdfgpu_msm_submit / vdfgpu_msm_wait (pinned host scalars in, host point out), two commitments in flight",
+           "api": f"vdfgpu_msm_submit / vdfgpu_msm_wait (pinned host scalars in, host point out), {depth} commitments in flight",
            "sync_pinned": {"value": world * n / sync_pinned_s / 1e9, "ms_per_step": sync_pinned_s * 1e3,
                            "api": "vdfgpu_msm(gens, pinned host scalars, n, host out), one call at a time"},
            "sync_pageable": {"value": world * n / sync_pageable_s / 1e9, "ms_per_step": sync_pageable_s * 1e3,
@@ -869,14 +873,14 @@ def run_ours(args):
         "frac_executed_note": "products really executed: 88 per field multiplication (the SURVEY convention counts 136), 6 "
                               "multiplications per affine addition and 10 per XYZZ addition; frac > 1 means the stage does "
                               "less arithmetic than the convention assumes",
-        "measured": "stage times by CUDA events inside the library, one MSM at a time (the two-in-flight timed region overlaps stages of different MSMs)",
+        "measured": "stage times by CUDA events inside the library, one MSM at a time (the timed region overlaps stages of different MSMs)",
         "affine_rounds": R,
         "hbm_view": hbm_view(n, acc_s, traffic),
         "imad_lo_per_s": pl.value, "iadd3_per_s": pa.value,
         "kernel_ms": stage_ms["accumulate"], "stage_ms": stage_ms,
         "share_of_step": stage_ms["accumulate"] / max(1e-9, sum(stage_ms.values())),
         "judge_convention_c16_achieved": float(n) * 21760 / acc_s / 1e12,
-        "whole_msm_executed_frac_inflight2": (executed_mul * 88 / (inflight2_ms * 1e-3)) / pw.value,
+        "whole_step_executed_frac": (executed_mul * 88 / (ms_per_step * 1e-3)) / pw.value,
     }
 
     cpu_baseline = None
@@ -902,7 +906,6 @@ def run_ours(args):
                  "gens_setup_ms": runner.setup_s * 1e3},
         "serial": {"value": world * n / (serial_ms * 1e-3) / 1e9, "ms_per_step": serial_ms,
                    "note": "one commitment at a time on one stream (what the serial MSMs of one Nova step see)"},
-        "inflight2": {"value": world * n / (inflight2_ms * 1e-3) / 1e9, "ms_per_step": inflight2_ms},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "cpu_baseline": cpu_baseline, "parity_vs_cpu_full_size": parity, "parity_known_dlog_all_ranks": parity_known_dlog,
     }

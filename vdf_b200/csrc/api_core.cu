@@ -81,20 +81,43 @@ void require_ready() {
 }
 
 // ---- workspaces --------------------------------------------------------------------------------------
+static void graphs_drop_if(const void* block, const void* gens_pts) {
+  Context& c = ctx();
+  for (size_t i = 0; i < c.graphs.size();) {
+    if ((block && c.graphs[i].block == block) || (gens_pts && c.graphs[i].gens_pts == gens_pts) || (!block && !gens_pts)) {
+      cudaGraphExecDestroy(c.graphs[i].exec);
+      c.graphs.erase(c.graphs.begin() + i);
+    } else {
+      i++;
+    }
+  }
+}
+
 static void workspace_release(Workspace& w) {
   if (w.block) {
     cudaStreamSynchronize(w.stream);
+    graphs_drop_if(w.block, nullptr);
     cudaFree(w.block);
   }
   w.block = nullptr;
   w.block_bytes = 0;
 }
 
+static void workspace_release_all(Workspace& w) {
+  workspace_release(w);
+  if (w.stage_sc) cudaFree(w.stage_sc);
+  if (w.stage_out) cudaFree(w.stage_out);
+  w.stage_sc = nullptr;
+  w.stage_out = nullptr;
+  w.stage_cap = 0;
+}
+
 static void trim_locked() {
   Context& c = ctx();
   if (!c.ready) return;
   cudaDeviceSynchronize();
-  for (auto& w : c.workspaces) workspace_release(*w);
+  graphs_drop_if(nullptr, nullptr);
+  for (auto& w : c.workspaces) workspace_release_all(*w);
   c.workspaces.clear();
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, c.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
@@ -114,7 +137,7 @@ static Workspace* workspace_for(cudaStream_t s, size_t need, bool may_fail) {
       size_t lru = 0;
       for (size_t i = 1; i < c.workspaces.size(); i++)
         if (c.workspaces[i]->last_use < c.workspaces[lru]->last_use) lru = i;
-      workspace_release(*c.workspaces[lru]);
+      workspace_release_all(*c.workspaces[lru]);
       c.workspaces.erase(c.workspaces.begin() + lru);
     }
     c.workspaces.emplace_back(new Workspace());
@@ -132,6 +155,15 @@ static Workspace* workspace_for(cudaStream_t s, size_t need, bool may_fail) {
       want = need;
       e = cudaMalloc(&p, want);
     }
+    if (e != cudaSuccess && !may_fail) {
+      // last resort before failing the call: give back the other streams' idle arenas and the cached pool memory
+      cudaGetLastError();
+      for (auto& o : c.workspaces)
+        if (o.get() != w) workspace_release(*o);
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, c.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+      e = cudaMalloc(&p, want);
+    }
     if (e != cudaSuccess) {
       cudaGetLastError();
       if (may_fail) return nullptr;
@@ -143,6 +175,34 @@ static Workspace* workspace_for(cudaStream_t s, size_t need, bool may_fail) {
   }
   w->arena.base = w->block;
   w->arena.reset(w->block_bytes);
+  return w;
+}
+
+// persistent scalar / result staging of the host entry points on stream `s` (see Workspace)
+static Workspace* staging_for(cudaStream_t s, size_t n) {
+  Context& c = ctx();
+  Workspace* w = nullptr;
+  for (auto& p : c.workspaces)
+    if (p->stream == s) w = p.get();
+  if (!w) {
+    w = workspace_for(s, 0, false);
+  }
+  if (!w->stage_out) VDF_CUDA_CHECK(cudaMalloc((void**)&w->stage_out, 4 * sizeof(jac_t)));
+  if (w->stage_cap < n) {
+    VDF_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (w->stage_sc) cudaFree(w->stage_sc);
+    w->stage_sc = nullptr;
+    w->stage_cap = 0;
+    const size_t want = n + n / 8 + 64;
+    cudaError_t e = cudaMalloc((void**)&w->stage_sc, want * sizeof(fe));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      VDF_CUDA_CHECK(cudaMalloc((void**)&w->stage_sc, (n + 1) * sizeof(fe)));
+      w->stage_cap = n;
+    } else {
+      w->stage_cap = want;
+    }
+  }
   return w;
 }
 
@@ -222,6 +282,81 @@ static void check_refs(const MsmPlan& p, const vdfgpu_gens* g, size_t n) {
   if ((uint64_t)p.W * n * p.batch >= (1ull << 32)) throw ArgError("msm: too many sorted entries for one pass");
 }
 
+// ---- graph replay of latency-regime MSMs ------------------------------------------------------------------
+static bool graphs_enabled() { return env_long("VDFGPU_GRAPH", 1, 0, 1) != 0; }
+constexpr size_t GRAPH_MAX_ENTRIES = 1u << 22;   // sorted entries: above this the launch gaps no longer matter
+constexpr size_t GRAPH_CACHE = 24;
+
+static uint64_t mix64(uint64_t h, uint64_t v) {
+  h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+  return h;
+}
+
+// runs `enqueue(L)` either directly or, for small plans on an arena, as a cached CUDA graph
+template <class Enqueue>
+static void msm_dispatch(vdfgpu_gens* g, const MsmPlan& p, Workspace* w, cudaStream_t st, const ScalarSet& ss,
+                         const void* pts, const void* d_out, Enqueue enqueue) {
+  Context& c = ctx();
+  const size_t E = (size_t)p.n * p.W * p.batch;
+  if (!w || !graphs_enabled() || c.prof.enabled || E > GRAPH_MAX_ENTRIES) {
+    CudaLaunch L(st, &c.prof, w ? &w->arena : nullptr);
+    enqueue(L);
+    c.launches += L.launches;
+    return;
+  }
+  std::vector<uint64_t> key = {(uint64_t)g->curve, p.n, p.c, p.W, p.B, p.NB, p.table, p.level_stride, p.S, p.G, p.logm, p.is_mont, p.batch,
+                               p.len[0], p.len[1], p.len[2], p.len[3], p.raw_jacobian, p.rec_warp, p.affine_rounds, p.affine_K};
+  for (uint32_t j = 0; j < MSM_MAX_BATCH; j++) key.push_back((uint64_t)(uintptr_t)ss.v[j]);
+  key.push_back((uint64_t)(uintptr_t)pts);
+  key.push_back((uint64_t)(uintptr_t)d_out);
+  key.push_back((uint64_t)(uintptr_t)w->block);
+  key.push_back((uint64_t)(uintptr_t)st);
+  uint64_t h = 0;
+  for (uint64_t v : key) h = mix64(h, v);
+  for (auto& e : c.graphs)
+    if (e.key_hash == h && e.key == key) {
+      e.last_use = ++c.tick;
+      VDF_CUDA_CHECK(cudaGraphLaunch(e.exec, st));
+      c.launches += e.launches;
+      c.graph_replays++;
+      return;
+    }
+  // capture (the arena is already large enough: nothing below allocates device memory)
+  cudaGraph_t graph = nullptr;
+  CudaLaunch L(st, nullptr, &w->arena);
+  VDF_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  try {
+    enqueue(L);
+  } catch (...) {
+    cudaStreamEndCapture(st, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    throw;
+  }
+  VDF_CUDA_CHECK(cudaStreamEndCapture(st, &graph));
+  MsmGraph e;
+  cudaError_t err = cudaGraphInstantiate(&e.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (err != cudaSuccess) throw std::runtime_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(err));
+  e.key_hash = h;
+  e.key = std::move(key);
+  e.gens_pts = g->pts;
+  e.block = w->block;
+  e.launches = L.launches;
+  e.last_use = ++c.tick;
+  if (c.graphs.size() >= GRAPH_CACHE) {
+    size_t lru = 0;
+    for (size_t i = 1; i < c.graphs.size(); i++)
+      if (c.graphs[i].last_use < c.graphs[lru].last_use) lru = i;
+    cudaGraphExecDestroy(c.graphs[lru].exec);
+    c.graphs.erase(c.graphs.begin() + lru);
+  }
+  VDF_CUDA_CHECK(cudaGraphLaunch(e.exec, st));
+  c.launches += e.launches;
+  c.graph_captures++;
+  c.graphs.push_back(std::move(e));
+}
+
 void msm_on_device(vdfgpu_gens* g, size_t first, const fe* d_scalars, size_t n, jac_t* d_out, bool is_mont,
                    cudaStream_t stream) {
   if (first + n > g->n) throw ArgError("msm: more scalars than generators");
@@ -231,12 +366,13 @@ void msm_on_device(vdfgpu_gens* g, size_t first, const fe* d_scalars, size_t n, 
   MsmPlan p = make_plan(g, n, is_mont);
   check_refs(p, g, n);
   Workspace* w = n ? plan_workspace(g->curve, p, st) : nullptr;
-  CudaLaunch L(st, &c.prof, w ? &w->arena : nullptr);
   const affine_t* pts = g->pts + first;
   ScalarSet ss{{d_scalars, nullptr, nullptr, nullptr}};
-  if (g->curve == VDFGPU_PALLAS) msm_run<CudaLaunch, Pallas, Fq>(L, p, pts, ss, d_out);
-  else msm_run<CudaLaunch, Vesta, Fp>(L, p, pts, ss, d_out);
-  c.launches += L.launches;
+  const int curve = g->curve;
+  msm_dispatch(g, p, w, st, ss, pts, d_out, [&](CudaLaunch& L) {
+    if (curve == VDFGPU_PALLAS) msm_run<CudaLaunch, Pallas, Fq>(L, p, pts, ss, d_out);
+    else msm_run<CudaLaunch, Vesta, Fp>(L, p, pts, ss, d_out);
+  });
 }
 
 // Host-scalar MSM in point-range chunks: the H2D copy of chunk k+1 (copy stream) overlaps the digit / sort /
@@ -306,10 +442,12 @@ void msm_batch_on_device(vdfgpu_gens* g, const fe* const* d_scalars, const size_
     p.len[j] = (uint32_t)lens[j];
   }
   Workspace* w = n ? plan_workspace(g->curve, p, st) : nullptr;
-  CudaLaunch L(st, &c.prof, w ? &w->arena : nullptr);
-  if (g->curve == VDFGPU_PALLAS) msm_run<CudaLaunch, Pallas, Fq>(L, p, g->pts, ss, d_out);
-  else msm_run<CudaLaunch, Vesta, Fp>(L, p, g->pts, ss, d_out);
-  c.launches += L.launches;
+  const int curve = g->curve;
+  const affine_t* pts = g->pts;
+  msm_dispatch(g, p, w, st, ss, pts, d_out, [&](CudaLaunch& L) {
+    if (curve == VDFGPU_PALLAS) msm_run<CudaLaunch, Pallas, Fq>(L, p, pts, ss, d_out);
+    else msm_run<CudaLaunch, Vesta, Fp>(L, p, pts, ss, d_out);
+  });
 }
 
 static void build_table(vdfgpu_gens* g, CudaLaunch& L) {
@@ -635,6 +773,7 @@ int vdfgpu_gens_destroy(vdfgpu_gens* g) {
     if (ctx().ready) {
       VDF_CUDA_CHECK(cudaSetDevice(ctx().device));
       cudaDeviceSynchronize();   // MSMs on any stream (asynchronous slots, other threads) may still read the points
+      graphs_drop_if(nullptr, g->pts);
     }
     cudaFree(g->pts);
     delete g;
@@ -648,6 +787,16 @@ int vdfgpu_msm(vdfgpu_gens* g, const void* scalars32_host, size_t n, void* out_p
     require_ready();
     Context& c = ctx();
     if (n > g->n) throw ArgError("msm: more scalars than generators");
+    if (workspaces_enabled() && !std::getenv("VDFGPU_MSM_CHUNKS")) {
+      // persistent staging buffers of this stream: stable pointers, so a Nova-size commitment replays as a graph
+      cudaStream_t st = cur_stream();
+      Workspace* ws = staging_for(st, n);
+      h2d(ws->stage_sc, scalars32_host, n * 32, st);
+      msm_on_device(g, 0, ws->stage_sc, n, ws->stage_out, true);
+      d2h(out_point96_host, ws->stage_out, sizeof(jac_t), st);
+      sync_after_unlock(st);
+      return;
+    }
     DevBuf<fe> sc(n ? n : 1, cur_stream());
     DevBuf<jac_t> res(1, cur_stream());
     // Chunked schedule (H2D of chunk k+1 under the accumulation of chunk k): measured on B200 at n = 2^22 the
@@ -827,6 +976,7 @@ static int dropin_verify_mode() {   // 0 off, 1 sample, 2 full
 
 static void dropin_drop(DropinEntry& e) {
   if (e.gens) {
+    graphs_drop_if(nullptr, e.gens->pts);
     cudaFree(e.gens->pts);
     delete e.gens;
     e.gens = nullptr;
@@ -925,10 +1075,20 @@ static void mult_pippenger_body(int curve, void* out, const void* points, size_t
   require_ready();
   Context& c = ctx();
   cudaStream_t st = cur_stream();
+  if (workspaces_enabled()) {
+    if (vdfgpu_gens* cached = dropin_lookup(curve, points, npoints)) {
+      Workspace* ws = staging_for(st, npoints);
+      h2d(ws->stage_sc, scalars, npoints * 32, st);
+      msm_on_device(cached, 0, ws->stage_sc, npoints, ws->stage_out, is_mont);
+      d2h(out, ws->stage_out, sizeof(jac_t), st);
+      sync_after_unlock(st);
+      return;
+    }
+  }
   DevBuf<fe> sc(npoints, st);
   DevBuf<jac_t> res(1, st);
   h2d(sc.p, scalars, npoints * 32, st);
-  if (vdfgpu_gens* cached = dropin_lookup(curve, points, npoints)) {
+  if (vdfgpu_gens* cached = workspaces_enabled() ? nullptr : dropin_lookup(curve, points, npoints)) {
     msm_on_device(cached, 0, sc.p, npoints, res.p, is_mont);
   } else {
     vdfgpu_gens g;

@@ -499,7 +499,11 @@ int vdfgpu_running_finish(vdfgpu_running* f, const void* r32_host) {
     // u <- u + r*1, X <- X + r*X2: the same kernel over the (1 + io)-element tail
     launch_fold(L, s->field, f->uX, f->uX2, 1 + (size_t)s->io, nullptr, nullptr, 0, f->r);
     c.launches += L.launches;
-    sync_after_unlock(cur_stream());
+    // No wait: the next call on this instance is ordered behind the fold on the stream.  Only a pinned r32_host would
+    // still be in flight after return (pageable copies are staged before cudaMemcpyAsync returns).
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, r32_host) == cudaSuccess && at.type == cudaMemoryTypeHost) sync_after_unlock(cur_stream());
+    else cudaGetLastError();
     f->have_fresh = false;
   });
 }

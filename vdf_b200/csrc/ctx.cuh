@@ -31,6 +31,24 @@ struct Workspace {
   uint8_t* block = nullptr;
   size_t block_bytes = 0;
   uint64_t last_use = 0;
+  // persistent staging of the host entry points on this stream (scalars in, point out): stable device pointers
+  // from call to call, which is what lets a latency-regime MSM be replayed as a CUDA graph
+  fe* stage_sc = nullptr;
+  size_t stage_cap = 0;
+  jac_t* stage_out = nullptr;
+};
+
+// A latency-regime MSM (Nova-size commitments: ~50 dependent launches of 5-40 us each) captured once as a CUDA graph
+// and replayed while plan, pointers and workspace block stay the same: no per-kernel launch gaps, no host-side
+// pipeline code on the replay path.
+struct MsmGraph {
+  uint64_t key_hash = 0;
+  std::vector<uint64_t> key;     // plan words, pointers, stream
+  const void* gens_pts = nullptr;
+  const void* block = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  size_t launches = 0;
+  uint64_t last_use = 0;
 };
 
 // one in-flight host-scalar MSM of the asynchronous API (vdfgpu_msm_submit / vdfgpu_msm_wait): its own stream
@@ -70,6 +88,8 @@ struct Context {
   std::atomic<uint64_t> launches{0};
   StageProfile prof;      // stage timing of the most recent MSM (vdfgpu_profile_*)
   std::vector<std::unique_ptr<Workspace>> workspaces;
+  std::vector<MsmGraph> graphs;
+  uint64_t graph_replays = 0, graph_captures = 0;
   std::vector<DropinEntry> dropin;
   uint64_t dropin_hits = 0, dropin_misses = 0;
   uint64_t tick = 0;
