@@ -56,6 +56,10 @@ struct MsmPlan {
 
 constexpr uint32_t MSM_MAX_BATCH = 4;
 
+#ifndef VDF_ACC_MINB
+#define VDF_ACC_MINB 5   // resident blocks per SM the XYZZ accumulation kernel is compiled for (96 registers)
+#endif
+
 struct ScalarSet {
   const fe* v[MSM_MAX_BATCH];
 };
@@ -750,7 +754,7 @@ void msm_accumulate(L& L_, const MsmPlan& p, const affine_t* pts, const ScalarSe
     if (s2 < 32) s2 = 32;
     if (s2 < S) S = (uint32_t)s2;
   }
-  S = fit_waves(e_cap, S, (size_t)148 * 5 * 128);   // a few waves of ranges: no partly filled last wave
+  S = fit_waves(e_cap, S, (size_t)148 * VDF_ACC_MINB * 128);   // a few waves of ranges: no partly filled last wave
 
   // accumulate over fixed-size ranges of the sorted list
   size_t T_acc = (e_cap + S - 1) / S;
@@ -758,10 +762,10 @@ void msm_accumulate(L& L_, const MsmPlan& p, const affine_t* pts, const ScalarSe
   RecHdr* hdr_a = L_.template alloc<RecHdr>(n_rec);
   xyzz_t* pt_a = L_.template alloc<xyzz_t>(n_rec);
   if (p.affine_rounds)
-    L_.template run<128, 5>(T_acc, AccumulateFn<C, true>{alist_offs, NBK, nullptr, nullptr, alist_x, alist_y, buckets,
+    L_.template run<128, VDF_ACC_MINB>(T_acc, AccumulateFn<C, true>{alist_offs, NBK, nullptr, nullptr, alist_x, alist_y, buckets,
                                                          hdr_a, pt_a, S});
   else
-    L_.template run<128, 5>(T_acc, AccumulateFn<C>{offs, NBK, sref, pts, nullptr, nullptr, buckets, hdr_a, pt_a, S});
+    L_.template run<128, VDF_ACC_MINB>(T_acc, AccumulateFn<C>{offs, NBK, sref, pts, nullptr, nullptr, buckets, hdr_a, pt_a, S});
   L_.free(alist_x); L_.free(alist_offs);
 
   // segmented reduction of the records: log-depth levels, then owners

@@ -176,7 +176,10 @@ template <class F>
 struct BatchInvFn {
   fe* v;
   uint32_t n;
-  static constexpr uint32_t J = 32;
+#ifndef VDF_BATCHINV_J
+#define VDF_BATCHINV_J 32
+#endif
+  static constexpr uint32_t J = VDF_BATCHINV_J;
   VDF_HD void operator()(size_t u) const {
     const uint32_t lo = (uint32_t)u * J, hi = lo + J < n ? lo + J : n;
     fe pre[J];
