@@ -359,9 +359,10 @@ def nova_step_measurements(_lib, ts=(10, 100, 1000, 1024, 4096, 16384)):
             sec.set_running(sec_W, [0] * s_cons, N.RelaxedR1CSInstance(None, None, list(sec_X), 1))
             pri.set_running(W, [0] * cons, N.RelaxedR1CSInstance(None, None, list(X), 1))
 
+            rp = N.RecursiveProver(pri, sec)    # the public two-curve step (vdf_b200/nova.py)
+
             def step():
-                sec.prove_step_bytes(sWb, sXb, r_fixed)
-                pri.prove_step_bytes(Wb, Xb, r_fixed)
+                rp.prove_step_bytes(sWb, sXb, Wb, Xb, r_fixed, r_fixed)
 
             dt = timed(step)
             if not raw:
@@ -379,8 +380,7 @@ def nova_step_measurements(_lib, ts=(10, 100, 1000, 1024, 4096, 16384)):
                 k = [0]
 
                 def step_bank():
-                    sec.prove_step_bytes(sWb, sXb, r_fixed)
-                    pri.prove_step_bank_bytes(bank, k[0] & 3, off, holed, Xb, r_fixed)
+                    rp.prove_step_bytes(sWb, sXb, holed, Xb, r_fixed, r_fixed, bank=bank, step=k[0] & 3, step_offset=off)
                     k[0] += 1
 
                 dtb = timed(step_bank)
@@ -469,6 +469,51 @@ def dropin_measurements(lib, _lib, torch, sizes=(13904, 75344, 1 << 22)):
         _lib.check(lib.vdfgpu_dropin_cache_clear())
     out["note"] = "sample verification of the cached set (default VDFGPU_DROPIN_VERIFY=sample)"
     return out
+
+
+def sumcheck_measurements(lib, _lib, torch, ell=24):
+    """SURVEY 8f rank 2: the sum-check kernels of CompressedSNARK::prove on 2^24-entry tables (4 x 512 MiB, far beyond
+    L2): the first (largest) round's evaluation and bind kernels against the HBM roofline, and a whole ell-round cubic
+    sum-check with a trivial host callback (Nova's own tables have 2^14 - 2^17 entries and are launch-bound)."""
+    n = 1 << ell
+    tabs = [rand_fe_dev(torch, n) for _ in range(4)]
+    peak, src = hbm_peak()
+    r_host = (ctypes.c_uint64 * 4)(5, 0, 0, 0)
+    calls = []
+
+    def cb(_user, rnd, evals, n_evals, r_out):
+        calls.append(rnd)
+        ctypes.memmove(r_out, r_host, 32)
+        return 0
+
+    fn = _lib.ROUND_FN(cb)
+    final = (ctypes.c_uint8 * 128)()
+    # one round = evaluation (reads 4 tables) + bind (reads 4 tables, writes 4 half tables): time a 1-variable prefix
+    # by running the full sum-check and dividing is not possible, so time whole sum-checks: bytes = sum over rounds
+    reps = 3
+    times = []
+    for _ in range(reps + 1):
+        fresh = [t.clone() for t in tabs]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _lib.check(lib.vdfgpu_sumcheck_cubic_dev(1, *[t.data_ptr() for t in fresh], ell, ctypes.cast(fn, ctypes.c_void_p), None, final))
+        times.append(time.perf_counter() - t0)
+        del fresh
+    dt = min(times[1:])
+    # algorithmic bytes: round k (length n / 2^k): evaluation reads 4 tables, bind reads 4 and writes 4 halves
+    alg = sum(4 * 32 * (n >> k) + 4 * 32 * (n >> k) + 4 * 32 * (n >> (k + 1)) for k in range(ell))
+    quad = [rand_fe_dev(torch, n) for _ in range(2)]
+    t0 = time.perf_counter()
+    _lib.check(lib.vdfgpu_sumcheck_quad_dev(1, quad[0].data_ptr(), quad[1].data_ptr(), ell, ctypes.cast(fn, ctypes.c_void_p), None, final))
+    dq = time.perf_counter() - t0
+    algq = sum(2 * 32 * (n >> k) * 2 + 2 * 32 * (n >> (k + 1)) for k in range(ell))
+    return {"ell": ell, "entries": n, "rounds_called_back": len(calls) // (reps + 2),
+            "cubic": {"ms": dt * 1e3, "algorithmic_bytes": alg, "achieved_gbs": alg / dt / 1e9, "frac_of_hbm": alg / dt / 1e9 / peak,
+                      "field_mul_per_s": 10 * n / dt},
+            "quad": {"ms": dq * 1e3, "algorithmic_bytes": algq, "achieved_gbs": algq / dq / 1e9, "frac_of_hbm": algq / dq / 1e9 / peak},
+            "hbm_peak_gbs": peak, "hbm_peak_source": src,
+            "note": "wall clock of vdfgpu_sumcheck_*_dev on device-resident tables incl. one 96-byte D2H + host callback per round; "
+                    "the cubic round does 6 multiplications per 256 bytes and is multiply-bound before it is HBM-bound"}
 
 
 class MsmRunner:
@@ -590,6 +635,7 @@ def extra_measurements(lib, _lib, torch, args):
                      ("minroot_verify", lambda: minroot_verify_measurements(lib, _lib, torch)),
                      ("r1cs_hbm", lambda: r1cs_hbm_measurements(lib, _lib, torch)),
                      ("dropin", lambda: dropin_measurements(lib, _lib, torch)),
+                     ("sumcheck", lambda: sumcheck_measurements(lib, _lib, torch)),
                      ("gens_from_host", lambda: gens_from_host_cost(lib, _lib, torch))):
         try:
             t0 = time.perf_counter()

@@ -128,6 +128,12 @@ int vdfgpu_msm_batch_dev(vdfgpu_gens* g, const void* const* scalars32_dev, const
 /* point range [first, first+n) of the set: the shard a rank owns in the multi-GPU MSM */
 int vdfgpu_msm_range_dev(vdfgpu_gens* g, size_t first, const void* scalars32_dev, size_t n,
                          void* out_point96_dev);
+/* (X, Y, Z) -> (X / Z^2, Y / Z^3, 1) in place on `count` HOST points, computed on the host (no GPU needed): what the
+ * host entry points apply to their results after the copy has landed -- a field inversion is one sequential chain of
+ * ~335 multiplications, 0.12 ms in one GPU thread against ~15 us on a CPU core -- and what a caller applies to the
+ * un-normalised results of a VDFGPU_GENS_RAW_JACOBIAN set or of the _dev entry points when it wants canonical bytes.
+ * VDFGPU_HOST_NORMALISE=0 moves the normalisation of the host entry points back onto the device. */
+int vdfgpu_point_normalise_host(int curve, void* points96_host, size_t count);
 /* out = sum of k points (combining per-GPU partial results; also instance-side additions) */
 int vdfgpu_point_sum(int curve, const void* points96_host, size_t k, void* out_point96_host);
 
@@ -189,6 +195,32 @@ int vdfgpu_witness_bank_read(const vdfgpu_witness_bank* b, size_t first_step, si
 int vdfgpu_running_commit_step(vdfgpu_running* f, const vdfgpu_witness_bank* bank, size_t step, size_t step_offset,
                                const void* W2_host, const void* X2_host, void* comm_W2_point96_host,
                                void* comm_T_point96_host);
+
+/* ---- sum-check building blocks of CompressedSNARK::prove (src/nova/proof.rs:360-368 -> nova-snark 0.8
+ * spartan_with_ipa_pc; that crate is not under the reference tree: semantics restated in vdf_b200/csrc/sumcheck.cuh).
+ * Tables are multilinear polynomials in evaluation form, 2^ell field elements, most significant variable first.
+ *   eq_evals        out[idx] = prod_j (bit_j(idx) ? r_j : 1 - r_j)                      (EqPolynomial::evals)
+ *   sumcheck_cubic  ell rounds of prove_cubic_with_additive_term with comb(A,B,C,D) = A (B C - D): every round the
+ *                   library computes (e0, e2, e3), hands them to round_fn -- which owns the transcript: it forms the
+ *                   round polynomial from [e0, claim - e0, e2, e3], absorbs it, squeezes the challenge and writes it to
+ *                   r_out_fe32 (return 0; non-zero aborts with VDFGPU_ERR_STATE) -- and binds the top variable of all
+ *                   four tables to it.  final_evals receives A[0], B[0], C[0], D[0].  The tables are consumed.
+ *   sumcheck_quad   the same with comb(A,B) = A B and evaluations (e0, e2)               (prove_quad)
+ *   poly_evaluate   <eq(r), P>                                                          (MultilinearPolynomial::evaluate)
+ * round_fn runs on the calling thread, outside the library's lock. */
+typedef int (*vdfgpu_round_fn)(void* user, size_t round, const void* evals_fe32, size_t n_evals, void* r_out_fe32);
+int vdfgpu_eq_evals(int field, const void* r_host, size_t ell, void* out_host);
+int vdfgpu_eq_evals_dev(int field, const void* r_host, size_t ell, void* out_dev);
+int vdfgpu_sumcheck_cubic(int field, const void* A_host, const void* B_host, const void* C_host, const void* D_host,
+                          size_t ell, vdfgpu_round_fn round_fn, void* user, void* final_evals4_host);
+int vdfgpu_sumcheck_cubic_dev(int field, void* A_dev, void* B_dev, void* C_dev, void* D_dev, size_t ell,
+                              vdfgpu_round_fn round_fn, void* user, void* final_evals4_host);
+int vdfgpu_sumcheck_quad(int field, const void* A_host, const void* B_host, size_t ell, vdfgpu_round_fn round_fn,
+                         void* user, void* final_evals2_host);
+int vdfgpu_sumcheck_quad_dev(int field, void* A_dev, void* B_dev, size_t ell, vdfgpu_round_fn round_fn, void* user,
+                             void* final_evals2_host);
+int vdfgpu_poly_evaluate(int field, const void* poly_host, const void* r_host, size_t ell, void* out_host);
+int vdfgpu_poly_evaluate_dev(int field, const void* poly_dev, const void* r_host, size_t ell, void* out_host);
 
 /* ---- a8: batched MinRoot verification.  Replaces a loop of MinRootVDF::check (src/minroot.rs:369-371)
  * / Evaluation::verify (:424-426) over independent chains.  ok_out[k] = 1 iff

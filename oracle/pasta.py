@@ -607,3 +607,60 @@ def shape_to_coo_bytes(shape: R1CSShape):
         vals = fes_to_bytes([e[2] for e in M], shape.m)
         out.append((rows, cols, vals, len(M)))
     return out
+
+
+# ---- sum-check building blocks -------------------------------------------------------------
+# What CompressedSNARK::prove (src/nova/proof.rs:360-368) runs inside nova-snark 0.8's spartan_with_ipa_pc
+# (sumcheck.rs, polynomial.rs).  [R]: that crate is NOT under /root/reference; these are the mathematical
+# definitions of its EqPolynomial::evals, prove_cubic_with_additive_term, prove_quad, bound_poly_var_top and
+# MultilinearPolynomial::evaluate, restated from memory -- PARITY UNPINNED like the rest of this file.
+def eq_evals(r: Sequence[int], m: int) -> List[int]:
+    """eq[idx] = prod_j (bit_j(idx) ? r_j : 1 - r_j), r[0] <-> most significant bit of idx."""
+    out = [1]
+    for rj in r:
+        out = [v for e in out for v in (e * (1 - rj) % m, e * rj % m)]
+    return out
+
+
+def bind_top(P: Sequence[int], r: int, m: int) -> List[int]:
+    half = len(P) // 2
+    return [(P[i] + r * (P[half + i] - P[i])) % m for i in range(half)]
+
+
+def sumcheck_cubic_round(A, B, C, D, m: int):
+    """(e0, e2, e3) of one round with comb(A, B, C, D) = A (B C - D)."""
+    half = len(A) // 2
+    e = [0, 0, 0]
+    for i in range(half):
+        lo = (A[i], B[i], C[i], D[i])
+        hi = (A[half + i], B[half + i], C[half + i], D[half + i])
+        for k, t in enumerate((0, 2, 3)):
+            a, b, c, d = ((l + t * (h - l)) % m for l, h in zip(lo, hi))
+            e[k] = (e[k] + a * (b * c - d)) % m
+    return tuple(e)
+
+
+def sumcheck_quad_round(A, B, m: int):
+    half = len(A) // 2
+    e0 = sum(A[i] * B[i] for i in range(half)) % m
+    e2 = sum((2 * A[half + i] - A[i]) * (2 * B[half + i] - B[i]) for i in range(half)) % m
+    return e0, e2
+
+
+def sumcheck_prove(tables: Sequence[Sequence[int]], m: int, challenge):
+    """All rounds; `challenge(round, evals) -> r`.  Returns (per-round evals, challenges, final evaluations)."""
+    tabs = [list(t) for t in tables]
+    evals, rs = [], []
+    rnd = 0
+    while len(tabs[0]) > 1:
+        e = sumcheck_cubic_round(*tabs, m) if len(tabs) == 4 else sumcheck_quad_round(*tabs, m)
+        r = challenge(rnd, e)
+        evals.append(e)
+        rs.append(r)
+        tabs = [bind_top(t, r, m) for t in tabs]
+        rnd += 1
+    return evals, rs, [t[0] for t in tabs]
+
+
+def poly_evaluate(P: Sequence[int], r: Sequence[int], m: int) -> int:
+    return sum(a * b for a, b in zip(eq_evals(r, m), P)) % m

@@ -38,6 +38,12 @@ pub struct vdfgpu_witness_bank {
     _private: [u8; 0],
 }
 
+/// Per-round callback of the sum-check drivers: receives the round's evaluations (n_evals field elements), owns the
+/// transcript, writes the challenge to `r_out_fe32`, returns 0.
+pub type vdfgpu_round_fn = Option<
+    unsafe extern "C" fn(user: *mut c_void, round: size_t, evals_fe32: *const c_void, n_evals: size_t, r_out_fe32: *mut c_void) -> c_int,
+>;
+
 extern "C" {
     // ---- context
     pub fn vdfgpu_init(device: c_int) -> c_int;
@@ -80,6 +86,7 @@ extern "C" {
                                 out_points96_dev: *mut c_void) -> c_int;
     pub fn vdfgpu_msm_range_dev(g: *mut vdfgpu_gens, first: size_t, scalars32_dev: *const c_void, n: size_t,
                                 out_point96_dev: *mut c_void) -> c_int;
+    pub fn vdfgpu_point_normalise_host(curve: c_int, points96_host: *mut c_void, count: size_t) -> c_int;
     pub fn vdfgpu_point_sum(curve: c_int, points96_host: *const c_void, k: size_t,
                             out_point96_host: *mut c_void) -> c_int;
     pub fn vdfgpu_point_sum_dev(curve: c_int, points96_dev: *const c_void, k: size_t,
@@ -125,6 +132,24 @@ extern "C" {
     pub fn vdfgpu_running_commit_step(f: *mut vdfgpu_running, bank: *const vdfgpu_witness_bank, step: size_t,
                                       step_offset: size_t, w2_host: *const c_void, x2_host: *const c_void,
                                       comm_w2_point96_host: *mut c_void, comm_t_point96_host: *mut c_void) -> c_int;
+
+    // ---- sum-check building blocks (CompressedSNARK::prove)
+    pub fn vdfgpu_eq_evals(field: c_int, r_host: *const c_void, ell: size_t, out_host: *mut c_void) -> c_int;
+    pub fn vdfgpu_eq_evals_dev(field: c_int, r_host: *const c_void, ell: size_t, out_dev: *mut c_void) -> c_int;
+    pub fn vdfgpu_sumcheck_cubic(field: c_int, a_host: *const c_void, b_host: *const c_void, c_host: *const c_void,
+                                 d_host: *const c_void, ell: size_t, round_fn: vdfgpu_round_fn, user: *mut c_void,
+                                 final_evals4_host: *mut c_void) -> c_int;
+    pub fn vdfgpu_sumcheck_cubic_dev(field: c_int, a_dev: *mut c_void, b_dev: *mut c_void, c_dev: *mut c_void,
+                                     d_dev: *mut c_void, ell: size_t, round_fn: vdfgpu_round_fn, user: *mut c_void,
+                                     final_evals4_host: *mut c_void) -> c_int;
+    pub fn vdfgpu_sumcheck_quad(field: c_int, a_host: *const c_void, b_host: *const c_void, ell: size_t,
+                                round_fn: vdfgpu_round_fn, user: *mut c_void, final_evals2_host: *mut c_void) -> c_int;
+    pub fn vdfgpu_sumcheck_quad_dev(field: c_int, a_dev: *mut c_void, b_dev: *mut c_void, ell: size_t,
+                                    round_fn: vdfgpu_round_fn, user: *mut c_void, final_evals2_host: *mut c_void) -> c_int;
+    pub fn vdfgpu_poly_evaluate(field: c_int, poly_host: *const c_void, r_host: *const c_void, ell: size_t,
+                                out_host: *mut c_void) -> c_int;
+    pub fn vdfgpu_poly_evaluate_dev(field: c_int, poly_dev: *const c_void, r_host: *const c_void, ell: size_t,
+                                    out_host: *mut c_void) -> c_int;
 
     // ---- a8: batched MinRoot verification
     pub fn vdfgpu_minroot_check_batch(field: c_int, results_state96_host: *const c_void,

@@ -50,3 +50,24 @@ def test_encoding_roundtrip():
     pt = O.PALLAS.mul(5, O.PALLAS.gen)
     assert E.affine_to_bytes(pt, E.P) == O.affine_to_bytes(O.PALLAS, pt)
     assert E.point_from_bytes(O.jac_to_bytes(O.PALLAS, pt), E.P) == pt
+
+
+def test_point_normalise_host_matches_oracle():
+    """The host-side normalisation the host entry points apply to their results (vdfgpu_point_normalise_host, no GPU
+    needed): (X, Y, Z) -> (X / Z^2, Y / Z^3, 1) byte for byte, identity -> zeros, already-normalised unchanged."""
+    from oracle import pasta as O
+    lib = _lib.load()
+    rng = O.XorShiftRng()
+    for cv in (O.PALLAS, O.VESTA):
+        m = cv.base
+        buf, want = bytearray(), bytearray()
+        for k in range(20):
+            pt = cv.mul(O.field_random(rng, cv.order), cv.gen)
+            z = O.field_random(rng, m) if k else 1
+            buf += O.fe_to_bytes(pt[0] * z * z, m) + O.fe_to_bytes(pt[1] * z * z * z, m) + O.fe_to_bytes(z, m)
+            want += O.jac_to_bytes(cv, pt)
+        buf += O.fe_to_bytes(5, m) + O.fe_to_bytes(7, m) + bytes(32)      # Z = 0: the identity
+        want += bytes(96)
+        assert lib.vdfgpu_point_normalise_host(cv.cid, _lib.as_ptr(buf), 21) == 0
+        assert bytes(buf) == bytes(want)
+    assert lib.vdfgpu_point_normalise_host(7, None, 0) == -1

@@ -250,3 +250,44 @@ def test_workspace_arena_and_pool_agree(gpu_lib, monkeypatch):
         _lib.check(gpu_lib.vdfgpu_trim())
     monkeypatch.setenv("VDFGPU_WORKSPACE", "1")
     assert g.commit_bytes(sb) == a
+
+
+def test_recursive_prover_both_curves(gpu_lib):
+    """RecursiveSNARK::prove_step's data-parallel side on BOTH curves (src/nova/proof.rs:342-349; sizes of
+    test_nova_proof: t = 5, 3 steps): secondary (Vesta) then primary (Pallas) NIFS per step, device-resident running
+    instances, every folded instance compared with the oracle and checked with is_sat_relaxed."""
+    t, aug = 5, 48
+    insts = {}
+    for name, fid in (("pri", O.FIELD_FQ), ("sec", O.FIELD_FP)):
+        ovdf = O.MinRootVDF(fid)
+        st = O.State(O.field_random(O.XorShiftRng(), ovdf.m), 0, 1)
+        seq = []
+        for _ in range(4):
+            st = ovdf.eval(st, t)
+            seq.append(O.make_step_instance(fid, t if name == "pri" else 1, st, aug_cons=aug))
+        insts[name] = seq
+    provers, shapes, state = {}, {}, {}
+    for name, fid, cid in (("pri", O.FIELD_FQ, O.CURVE_PALLAS), ("sec", O.FIELD_FP, O.CURVE_VESTA)):
+        shape, W0, X0, _ = insts[name][0]
+        gs = N.R1CSShape(fid, shape.num_cons, shape.num_vars, shape.num_io, shape.A, shape.B, shape.C)
+        gens = G.Generators.progression(cid, 11, 3, max(shape.num_cons, shape.num_vars), table=True)
+        p = N.RunningProver(gs, gens)
+        p.set_running(W0, [0] * shape.num_cons, N.RelaxedR1CSInstance(gens.commit(W0), None, list(X0), 1))
+        provers[name], shapes[name] = p, shape
+        state[name] = (list(W0), [0] * shape.num_cons, 1, list(X0))
+    rp = N.RecursiveProver(provers["pri"], provers["sec"])
+    for k in range(1, 4):
+        (_, sW, sX, _), (_, pW, pX, _) = insts["sec"][k], insts["pri"][k]
+        (cT_s, r_s), (cT_p, r_p) = rp.prove_step(sW, sX, pW, pX)
+        for name, W2, X2, r, cT, cid in (("sec", sW, sX, r_s, cT_s, O.CURVE_VESTA), ("pri", pW, pX, r_p, cT_p, O.CURVE_PALLAS)):
+            shape, cv = shapes[name], O.CURVES[cid]
+            Wr, Er, ur, Xr = state[name]
+            T = shape.cross_term(Wr, ur, Xr, W2, X2)
+            assert cT == cv.msm_known_dlog(T, 11, 3)
+            state[name] = (O.fold_vec(Wr, W2, r, shape.m), O.fold_vec(Er, T, r, shape.m), (ur + r) % shape.m,
+                           [(a + r * b) % shape.m for a, b in zip(Xr, X2)])
+            assert provers[name].get_running() == state[name]
+            assert shape.is_sat_relaxed(*state[name])
+            assert provers[name].U.comm_W == cv.msm_known_dlog(state[name][0], 11, 3)
+    assert rp.steps == 3
+

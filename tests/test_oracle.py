@@ -177,3 +177,45 @@ def test_known_dlog_numpy_helper():
     raw = rs.randint(0, 1 << 32, size=(40000, 8), dtype=np.uint64).astype(np.uint32)
     want = sum(int.from_bytes(raw[i].tobytes(), "little") * (7 + (5 + i) * 11) for i in range(raw.shape[0]))
     assert known_dlog_scalar(raw, 7, 11, first=5) == want
+
+
+def test_sumcheck_oracle_is_a_sound_sumcheck():
+    """Self-consistency of the oracle's sum-check restatement: every round e0 + e1 = claim with the
+    cubic through (e0, e1, e2, e3), the final claim equals comb of the final evaluations, eq tables evaluate right."""
+    import random
+    m = O.Q
+    py = random.Random(3)
+    ell = 5
+    tabs = [[py.randrange(m) for _ in range(1 << ell)] for _ in range(4)]
+    claim = sum(a * (b * c - d) for a, b, c, d in zip(*tabs)) % m
+
+    def interp_eval(ys, x):      # Lagrange through x = 0, 1, 2, 3
+        tot = 0
+        for i, yi in enumerate(ys):
+            num = den = 1
+            for j in range(4):
+                if j != i:
+                    num = num * (x - j) % m
+                    den = den * (i - j) % m
+            tot += yi * num * pow(den, -1, m)
+        return tot % m
+
+    state = {"claim": claim}
+
+    def challenge(rnd, e):
+        e1 = (state["claim"] - e[0]) % m
+        r = py.randrange(m)
+        state["claim"] = interp_eval([e[0], e1, e[1], e[2]], r)
+        return r
+
+    evals, rs, final = O.sumcheck_prove(tabs, m, challenge)
+    assert len(evals) == ell and len(rs) == ell
+    a, b, c, d = final
+    assert state["claim"] == a * (b * c - d) % m
+    assert final == [O.poly_evaluate(t, rs, m) for t in tabs]
+    # eq table: eq(r, idx) and sum to one
+    r = [py.randrange(m) for _ in range(4)]
+    eq = O.eq_evals(r, m)
+    assert sum(eq) % m == 1
+    assert eq[0b1010] == r[0] * (1 - r[1]) * r[2] * (1 - r[3]) % m
+    assert O.eq_evals([], m) == [1]

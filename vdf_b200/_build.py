@@ -10,7 +10,7 @@ ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 LIBDIR = ROOT / "lib"
 LIB = LIBDIR / "libvdfgpu.so"
-SOURCES = ["api_core.cu", "api_r1cs.cu"]
+SOURCES = ["api_core.cu", "api_r1cs.cu", "api_sumcheck.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

@@ -52,6 +52,7 @@ PROTOTYPES = {
     "vdfgpu_msm_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "vdfgpu_msm_batch_dev": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_size_t), c_uint32, c_void_p]),
     "vdfgpu_msm_range_dev": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
+    "vdfgpu_point_normalise_host": (c_int, [c_int, c_void_p, c_size_t]),
     "vdfgpu_point_sum": (c_int, [c_int, c_void_p, c_size_t, c_void_p]),
     "vdfgpu_r1cs_create": (c_int, [c_int, c_size_t, c_size_t, c_size_t,
                                    c_void_p, c_void_p, c_void_p, c_size_t,
@@ -70,6 +71,14 @@ PROTOTYPES = {
     "vdfgpu_running_get": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vdfgpu_running_commit": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vdfgpu_running_finish": (c_int, [c_void_p, c_void_p]),
+    "vdfgpu_eq_evals": (c_int, [c_int, c_void_p, c_size_t, c_void_p]),
+    "vdfgpu_eq_evals_dev": (c_int, [c_int, c_void_p, c_size_t, c_void_p]),
+    "vdfgpu_sumcheck_cubic": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "vdfgpu_sumcheck_cubic_dev": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "vdfgpu_sumcheck_quad": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "vdfgpu_sumcheck_quad_dev": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "vdfgpu_poly_evaluate": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vdfgpu_poly_evaluate_dev": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vdfgpu_minroot_check_batch": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_uint64, c_size_t, c_void_p]),
     "vdfgpu_minroot_check_batch_dev": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_uint64, c_size_t, c_void_p]),
     "vdfgpu_minroot_inverse_eval_batch": (c_int, [c_int, c_void_p, c_uint64, c_size_t, c_void_p]),
@@ -77,6 +86,10 @@ PROTOTYPES = {
     "vdfgpu_field_mul_batch": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_uint32, c_void_p]),
     "vdfgpu_imad_peak": (c_int, [POINTER(c_double), POINTER(c_double), POINTER(c_double)]),
 }
+
+
+# int (*vdfgpu_round_fn)(void* user, size_t round, const void* evals_fe32, size_t n_evals, void* r_out_fe32)
+ROUND_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p)
 
 
 def lib_path() -> Path:

@@ -29,19 +29,96 @@ void sync_after_unlock(cudaStream_t s) {
   t_wait_ev = t_sync_ev;
 }
 
-void wait_pending_sync() {
-  cudaEvent_t ev = t_wait_ev;
-  if (!ev) return;
-  t_wait_ev = nullptr;
-  VDF_CUDA_CHECK(cudaEventSynchronize(ev));
-}
-
 static long env_long(const char* name, long dflt, long lo, long hi) {
   const char* s = std::getenv(name);
   if (!s || !*s) return dflt;
   long v = std::atol(s);
   return v < lo ? lo : (v > hi ? hi : v);
 }
+
+// ---- host-side normalisation of returned points (see ctx.cuh) ----------------------------------------------------
+namespace hostfield {
+typedef unsigned __int128 u128;
+struct Mod { uint64_t m[4], one[4], inv; };   // modulus, R mod m, -m^-1 mod 2^64
+static const Mod FP_MOD = {{0x992d30ed00000001ull, 0x224698fc094cf91bull, 0x0000000000000000ull, 0x4000000000000000ull},
+                           {0x34786d38fffffffdull, 0x992c350be41914adull, 0xffffffffffffffffull, 0x3fffffffffffffffull},
+                           0x992d30ecffffffffull};
+static const Mod FQ_MOD = {{0x8c46eb2100000001ull, 0x224698fc0994a8ddull, 0x0000000000000000ull, 0x4000000000000000ull},
+                           {0x5b2b3e9cfffffffdull, 0x992c350be3420567ull, 0xffffffffffffffffull, 0x3fffffffffffffffull},
+                           0x8c46eb20ffffffffull};
+
+static void mul(uint64_t* r, const uint64_t* a, const uint64_t* b, const Mod& f) {   // Montgomery CIOS, 4 x 64
+  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) { c += (u128)a[j] * b[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+    c += t[4]; t[4] = (uint64_t)c; t[5] = (uint64_t)(c >> 64);
+    const uint64_t q = t[0] * f.inv;
+    c = ((u128)q * f.m[0] + t[0]) >> 64;
+    for (int j = 1; j < 4; j++) { c += (u128)q * f.m[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+    c += t[4]; t[3] = (uint64_t)c; t[4] = t[5] + (uint64_t)(c >> 64);
+  }
+  uint64_t s[4];
+  u128 bw = 0;
+  for (int j = 0; j < 4; j++) { u128 d = (u128)t[j] - f.m[j] - (uint64_t)bw; s[j] = (uint64_t)d; bw = (d >> 64) & 1; }
+  const bool ge = t[4] != 0 || bw == 0;
+  for (int j = 0; j < 4; j++) r[j] = ge ? s[j] : t[j];
+}
+
+static void inv(uint64_t* r, const uint64_t* a, const Mod& f) {   // a^(m-2)
+  uint64_t e[4] = {f.m[0] - 2, f.m[1], f.m[2], f.m[3]};
+  uint64_t acc[4];
+  std::memcpy(acc, f.one, 32);
+  for (int i = 255; i >= 0; i--) {
+    mul(acc, acc, acc, f);
+    if ((e[i >> 6] >> (i & 63)) & 1) mul(acc, acc, a, f);
+  }
+  std::memcpy(r, acc, 32);
+}
+
+// (X, Y, Z) Jacobian, Montgomery limbs -> (X / Z^2, Y / Z^3, 1), or all zero for the identity
+static void normalise(uint8_t* p96, int curve) {
+  const Mod& f = curve == VDFGPU_PALLAS ? FP_MOD : FQ_MOD;
+  uint64_t X[4], Y[4], Z[4];
+  std::memcpy(X, p96, 32); std::memcpy(Y, p96 + 32, 32); std::memcpy(Z, p96 + 64, 32);
+  if ((Z[0] | Z[1] | Z[2] | Z[3]) == 0) {
+    std::memset(p96, 0, 96);
+    return;
+  }
+  uint64_t zi[4], zi2[4], zi3[4];
+  inv(zi, Z, f);
+  mul(zi2, zi, zi, f);
+  mul(zi3, zi2, zi, f);
+  mul(X, X, zi2, f);
+  mul(Y, Y, zi3, f);
+  std::memcpy(p96, X, 32); std::memcpy(p96 + 32, Y, 32); std::memcpy(p96 + 64, f.one, 32);
+}
+}  // namespace hostfield
+
+struct PendingNorm { void* p; size_t count; int curve; };
+static thread_local std::vector<PendingNorm> t_norms;
+
+void normalise_after_sync(void* host_ptr, size_t count, int curve) { t_norms.push_back({host_ptr, count, curve}); }
+
+bool host_normalise_wanted(const vdfgpu_gens* g) {
+  return !(g->flags & VDFGPU_GENS_RAW_JACOBIAN) && env_long("VDFGPU_HOST_NORMALISE", 1, 0, 1) != 0;
+}
+
+void discard_pending_sync() {
+  t_wait_ev = nullptr;
+  t_norms.clear();
+}
+
+void wait_pending_sync() {
+  cudaEvent_t ev = t_wait_ev;
+  t_wait_ev = nullptr;
+  std::vector<PendingNorm> norms;
+  norms.swap(t_norms);
+  if (ev) VDF_CUDA_CHECK(cudaEventSynchronize(ev));
+  for (const PendingNorm& n : norms)
+    for (size_t k = 0; k < n.count; k++) hostfield::normalise(reinterpret_cast<uint8_t*>(n.p) + 96 * k, n.curve);
+}
+
 
 static void init_locked(int device) {
   Context& c = ctx();
@@ -61,6 +138,7 @@ static void init_locked(int device) {
                              std::to_string(prop.major) + "." + std::to_string(prop.minor));
   VDF_CUDA_CHECK(upload_field_constants());
   upload_constants_r1cs();
+  upload_constants_sumcheck();
   VDF_CUDA_CHECK(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
   VDF_CUDA_CHECK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
   for (auto& e : c.chunk_ev) VDF_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -358,12 +436,13 @@ static void msm_dispatch(vdfgpu_gens* g, const MsmPlan& p, Workspace* w, cudaStr
 }
 
 void msm_on_device(vdfgpu_gens* g, size_t first, const fe* d_scalars, size_t n, jac_t* d_out, bool is_mont,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, bool raw) {
   if (first + n > g->n) throw ArgError("msm: more scalars than generators");
   Context& c = ctx();
   cudaStream_t st = stream ? stream : cur_stream();
   c.prof.n_marks = 0;
   MsmPlan p = make_plan(g, n, is_mont);
+  if (raw) p.raw_jacobian = 1;
   check_refs(p, g, n);
   Workspace* w = n ? plan_workspace(g->curve, p, st) : nullptr;
   const affine_t* pts = g->pts + first;
@@ -424,7 +503,8 @@ void msm_host_chunked(vdfgpu_gens* g, const void* h_scalars, size_t n, jac_t* d_
 
 // k scalar vectors over the same generators in ONE pass of the pipeline (one bucket set per vector):
 // the latency of one MSM for k commitments.  d_out receives k points.
-void msm_batch_on_device(vdfgpu_gens* g, const fe* const* d_scalars, const size_t* lens, uint32_t k, jac_t* d_out) {
+void msm_batch_on_device(vdfgpu_gens* g, const fe* const* d_scalars, const size_t* lens, uint32_t k, jac_t* d_out,
+                         bool raw) {
   if (k == 0 || k > MSM_MAX_BATCH) throw ArgError("msm_batch: batch size must be 1..4");
   size_t n = 0;
   for (uint32_t j = 0; j < k; j++) {
@@ -435,6 +515,7 @@ void msm_batch_on_device(vdfgpu_gens* g, const fe* const* d_scalars, const size_
   cudaStream_t st = cur_stream();
   c.prof.n_marks = 0;
   MsmPlan p = make_plan(g, n, true, k);
+  if (raw) p.raw_jacobian = 1;
   check_refs(p, g, n);
   ScalarSet ss{{nullptr, nullptr, nullptr, nullptr}};
   for (uint32_t j = 0; j < k; j++) {
@@ -792,9 +873,11 @@ int vdfgpu_msm(vdfgpu_gens* g, const void* scalars32_host, size_t n, void* out_p
       cudaStream_t st = cur_stream();
       Workspace* ws = staging_for(st, n);
       h2d(ws->stage_sc, scalars32_host, n * 32, st);
-      msm_on_device(g, 0, ws->stage_sc, n, ws->stage_out, true);
+      const bool hn = host_normalise_wanted(g);
+      msm_on_device(g, 0, ws->stage_sc, n, ws->stage_out, true, nullptr, hn);
       d2h(out_point96_host, ws->stage_out, sizeof(jac_t), st);
       sync_after_unlock(st);
+      if (hn) normalise_after_sync(out_point96_host, 1, g->curve);
       return;
     }
     DevBuf<fe> sc(n ? n : 1, cur_stream());
@@ -912,6 +995,19 @@ int vdfgpu_point_sum(int curve, const void* points96_host, size_t k, void* out_p
     c.launches += L.launches;
     sync_after_unlock(cur_stream());
   });
+}
+
+int vdfgpu_point_normalise_host(int curve, void* points96_host, size_t count) {
+  if (curve != VDFGPU_PALLAS && curve != VDFGPU_VESTA) {
+    set_error("point_normalise_host: unknown curve");
+    return VDFGPU_ERR_ARG;
+  }
+  if (count && !points96_host) {
+    set_error("point_normalise_host: null pointer");
+    return VDFGPU_ERR_ARG;
+  }
+  for (size_t k = 0; k < count; k++) hostfield::normalise(reinterpret_cast<uint8_t*>(points96_host) + 96 * k, curve);
+  return VDFGPU_OK;
 }
 
 int vdfgpu_point_sum_dev(int curve, const void* points96_dev, size_t k, void* out_point96_dev) {
@@ -1079,9 +1175,11 @@ static void mult_pippenger_body(int curve, void* out, const void* points, size_t
     if (vdfgpu_gens* cached = dropin_lookup(curve, points, npoints)) {
       Workspace* ws = staging_for(st, npoints);
       h2d(ws->stage_sc, scalars, npoints * 32, st);
-      msm_on_device(cached, 0, ws->stage_sc, npoints, ws->stage_out, is_mont);
+      const bool hn = host_normalise_wanted(cached);
+      msm_on_device(cached, 0, ws->stage_sc, npoints, ws->stage_out, is_mont, nullptr, hn);
       d2h(out, ws->stage_out, sizeof(jac_t), st);
       sync_after_unlock(st);
+      if (hn) normalise_after_sync(out, 1, curve);
       return;
     }
   }

@@ -198,12 +198,14 @@ int vdfgpu_commit_T(const vdfgpu_r1cs* s, vdfgpu_gens* gens, const void* W1_host
     h2d(uX2.p + 1, X2_host, io * 32, cur_stream());
     launch_cross_term(L, s, ZView{W1.p, uX1.p, uX1.p + 1}, ZView{W2.p, uX2.p, uX2.p + 1}, T.p);
     c.launches += L.launches;
+    const bool hn = gens && host_normalise_wanted(gens);
     if (gens) {
-      msm_on_device(gens, 0, T.p, nc, comm.p, true);
+      msm_on_device(gens, 0, T.p, nc, comm.p, true, nullptr, hn);
       d2h(comm_T_point96_host, comm.p, sizeof(jac_t), cur_stream());
     }
     if (T_host) d2h(T_host, T.p, nc * 32, cur_stream());
     sync_after_unlock(cur_stream());
+    if (hn) normalise_after_sync(comm_T_point96_host, 1, gens->curve);
   });
 }
 
@@ -361,10 +363,15 @@ static void running_commit_enqueue(vdfgpu_running* f, void* comm_W2_point96_host
   c.launches += L.launches;
   const fe* vecs[2] = {f->W2, f->T};
   const size_t lens[2] = {s->vars, s->cons};
-  msm_batch_on_device(f->gens, vecs, lens, 2, f->comm);
+  const bool hn = host_normalise_wanted(f->gens);
+  msm_batch_on_device(f->gens, vecs, lens, 2, f->comm, hn);
   d2h(comm_W2_point96_host, f->comm, sizeof(jac_t), st);
   d2h(comm_T_point96_host, f->comm + 1, sizeof(jac_t), st);
   sync_after_unlock(st);
+  if (hn) {
+    normalise_after_sync(comm_W2_point96_host, 1, f->gens->curve);
+    normalise_after_sync(comm_T_point96_host, 1, f->gens->curve);
+  }
   f->have_fresh = true;
 }
 

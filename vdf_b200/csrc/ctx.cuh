@@ -98,6 +98,7 @@ struct Context {
 Context& ctx();
 void set_error(const std::string& msg);
 void upload_constants_r1cs();   // api_r1cs.cu's copy of the constant-memory tables
+void upload_constants_sumcheck();   // api_sumcheck.cu's
 void require_ready();           // binds the calling thread to the library's device (lazy vdfgpu_init(0))
 
 // The stream a call enqueues on: the calling THREAD's stream (vdfgpu_set_stream is per thread) or the library's.
@@ -106,6 +107,7 @@ cudaStream_t cur_stream();
 // the context mutex is released, so other threads can enqueue meanwhile.
 void sync_after_unlock(cudaStream_t s);
 void wait_pending_sync();
+void discard_pending_sync();   // a failed call leaves nothing behind for the next one on this thread
 struct DeviceScope {   // restores the caller's current device on exit (the library binds its own for the call)
   int prev = -1;
   DeviceScope() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
@@ -166,12 +168,15 @@ int guarded(Body body) {
     wait_pending_sync();
     return VDFGPU_OK;
   } catch (const ArgError& e) {
+    discard_pending_sync();
     set_error(e.what());
     return VDFGPU_ERR_ARG;
   } catch (const StateError& e) {
+    discard_pending_sync();
     set_error(e.what());
     return VDFGPU_ERR_STATE;
   } catch (const std::exception& e) {
+    discard_pending_sync();
     set_error(e.what());
     return VDFGPU_ERR_CUDA;
   }
@@ -192,7 +197,17 @@ struct vdfgpu_gens {
 
 // internal cross-TU entry: MSM over device scalars into a device point, on the calling thread's stream
 namespace vdf {
+// raw = true: the result is written as an un-normalised Jacobian point whatever the set's flags say (the host entry
+// points then normalise it on the host, see normalise_after_sync)
 void msm_on_device(vdfgpu_gens* g, size_t first, const fe* d_scalars, size_t n, jac_t* d_out, bool is_mont,
-                   cudaStream_t stream = nullptr);
-void msm_batch_on_device(vdfgpu_gens* g, const fe* const* d_scalars, const size_t* lens, uint32_t k, jac_t* d_out);
+                   cudaStream_t stream = nullptr, bool raw = false);
+void msm_batch_on_device(vdfgpu_gens* g, const fe* const* d_scalars, const size_t* lens, uint32_t k, jac_t* d_out,
+                         bool raw = false);
+// Host entry points that return a point to HOST memory let the device write the un-normalised Jacobian result and
+// divide by Z on the host once the copy has landed: one field inversion is a strictly sequential chain of ~335
+// multiplications -- 0.12 ms in a single GPU thread, ~15 us on a CPU core -- and the bytes are identical.  (Same
+// split as the north star's: what cannot be parallelised stays on the host; Rust's to_affine() does this inversion on
+// the host for pasta-msm's results today.)  `count` consecutive 96-byte points at host_ptr, after the pending wait.
+void normalise_after_sync(void* host_ptr, size_t count, int curve);
+bool host_normalise_wanted(const vdfgpu_gens* g);
 }

@@ -224,3 +224,38 @@ class RunningProver:
             self.close()
         except Exception:
             pass
+
+
+class RecursiveProver:
+    """The GPU side of RecursiveSNARK::prove_step (src/nova/proof.rs:342-349) for BOTH curves of the cycle: per fold
+    step NIFS::prove on the secondary curve (Vesta: the instance produced by the previous step's secondary circuit is
+    folded into the secondary running instance), then NIFS::prove on the primary curve (Pallas: the step circuit's
+    fresh instance).  The two are strictly sequential -- the primary circuit's public input hashes the secondary
+    fold's output -- so this object only owns the two device-resident running instances and drives them in that
+    order; synthesis of the augmented circuits and the random oracle stay on the host (`challenge` is the labelled
+    stand-in)."""
+
+    def __init__(self, primary: RunningProver, secondary: RunningProver):
+        self.primary, self.secondary = primary, secondary
+        self.steps = 0
+
+    def prove_step(self, sec_W2: Sequence[int], sec_X2: Sequence[int], pri_W2: Sequence[int], pri_X2: Sequence[int],
+                   r_sec: Optional[int] = None, r_pri: Optional[int] = None):
+        """One fold step; returns ((comm_T_sec, r_sec), (comm_T_pri, r_pri))."""
+        a = self.secondary.prove_step(sec_W2, sec_X2, r_sec)
+        b = self.primary.prove_step(pri_W2, pri_X2, r_pri)
+        self.steps += 1
+        return a, b
+
+    def prove_step_bytes(self, sec_W2: bytes, sec_X2: bytes, pri_W2: bytes, pri_X2: bytes, r_sec: int, r_pri: int,
+                         bank: Optional[WitnessBank] = None, step: int = 0, step_offset: int = 0):
+        """Byte-level form (the timed region of the fold-steps/s benchmark).  With `bank`, the 4t+1 step variables of
+        the primary witness come from the device-resident witness bank."""
+        a = self.secondary.prove_step_bytes(sec_W2, sec_X2, r_sec)
+        if bank is None:
+            b = self.primary.prove_step_bytes(pri_W2, pri_X2, r_pri)
+        else:
+            b = self.primary.prove_step_bank_bytes(bank, step, step_offset, pri_W2, pri_X2, r_pri)
+        self.steps += 1
+        return a, b
+
