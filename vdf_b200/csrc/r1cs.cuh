@@ -81,12 +81,22 @@ struct CrossTermFn {
   VDF_HD void operator()(size_t idx) const {
     uint32_t row = (uint32_t)idx;
     const fe one = F::one(), minus_one = F::neg(F::one());
+    uint32_t ptr[3][2];
+#pragma unroll
+    for (uint32_t mat = 0; mat < 3; mat++) {   // six independent loads: one memory latency for all three matrices
+      ptr[mat][0] = m.row_ptr[mat * m.cons + row];
+      ptr[mat][1] = m.row_ptr[mat * m.cons + row + 1];
+    }
+    // (Measured and removed in round 2: prefetch.global.L2 of the later matrices' (col, val) entries and of the z
+    // elements they select, issued here -- 0.245 -> 0.283 ms on the 2^21-constraint shape.  The kernel is not bound by
+    // its chain of dependent loads: with full-size B coefficients a row costs 5 field multiplications for 252 bytes,
+    // i.e. 0.14 ms of multiply pipe against 0.08 ms of HBM for this shape)
     // the A and B products are combined as soon as both are known, so at most four dot products are live at once
     fe a1, a2, t;
+#pragma unroll
     for (uint32_t mat = 0; mat < 3; mat++) {
       fe s1 = F::zero(), s2 = F::zero();
-      uint32_t r = mat * m.cons + row;
-      uint32_t lo = m.row_ptr[r], hi = m.row_ptr[r + 1];
+      uint32_t lo = ptr[mat][0], hi = ptr[mat][1];
       for (uint32_t k = lo; k < hi; k++) {
         fe v = fe_load(m.val + k);
         uint32_t c = m.col[k];
