@@ -2,7 +2,7 @@
 //
 // Two ways to get the native code:
 //   VDFGPU_LIB_DIR=/path/to/vdf_b200/lib   link the libvdfgpu.so that `python -m vdf_b200._build` produced;
-//   otherwise                              compile vdf_b200/csrc/api_core.cu + api_r1cs.cu with nvcc through `cc`,
+//   otherwise                              compile vdf_b200/csrc/api_{core,r1cs,sumcheck}.cu with nvcc through `cc`,
 //                                          exactly the flags of vdf_b200/_build.py (sm_100a only, no fallback arch).
 use std::{env, path::PathBuf};
 
@@ -16,7 +16,7 @@ fn main() {
     }
     let root = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap()).join("../..");
     let csrc = root.join("vdf_b200/csrc");
-    for f in ["api_core.cu", "api_r1cs.cu"] {
+    for f in ["api_core.cu", "api_r1cs.cu", "api_sumcheck.cu"] {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
     println!("cargo:rerun-if-changed={}", root.join("include/vdfgpu.h").display());
@@ -32,6 +32,7 @@ fn main() {
         .flag("-fvisibility=hidden")
         .file(csrc.join("api_core.cu"))
         .file(csrc.join("api_r1cs.cu"))
+        .file(csrc.join("api_sumcheck.cu"))
         .compile("vdfgpu");
     println!("cargo:rustc-link-lib=dylib=stdc++");
 }

@@ -53,4 +53,4 @@ def test_pasta_msm_patch_links_the_library_and_symbols_match_the_wrapper():
     c = _c_decls()
     assert c["mult_pippenger_pallas"] == 5 and c["mult_pippenger_vesta"] == 5   # (out, points, npoints, scalars, is_mont)
     build = (ROOT / "rust" / "vdfgpu-sys" / "build.rs").read_text()
-    assert "arch=compute_100a,code=sm_100a" in build and "api_core.cu" in build and "api_r1cs.cu" in build
+    assert "arch=compute_100a,code=sm_100a" in build and "api_core.cu" in build and "api_r1cs.cu" in build and "api_sumcheck.cu" in build
