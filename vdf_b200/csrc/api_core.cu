@@ -2,6 +2,7 @@
 // See include/vdfgpu.h for the contract and the reference interfaces each entry point replaces.
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "ctx.cuh"
@@ -156,6 +157,67 @@ void require_ready() {
   if (!ctx().ready) init_locked(0);
   int cur = -1;
   if (cudaGetDevice(&cur) != cudaSuccess || cur != ctx().device) VDF_CUDA_CHECK(cudaSetDevice(ctx().device));
+}
+
+// ---- pageable uploads -----------------------------------------------------------------------------------
+void h2d_scalars(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (!bytes) return;
+  Context& c = ctx();
+  UploadStage& u = c.upload;
+  bool staged = bytes >= ((size_t)8 << 20) && env_long("VDFGPU_STAGED_UPLOAD", 1, 0, 1) != 0;
+  if (staged) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, src) != cudaSuccess) {
+      cudaGetLastError();
+      staged = false;
+    } else {
+      staged = at.type == cudaMemoryTypeUnregistered;   // pinned / managed / device sources: plain asynchronous copy
+    }
+  }
+  if (!staged) {
+    VDF_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return;
+  }
+  if (!u.ready) {
+    for (int t = 0; t < UploadStage::THREADS; t++)
+      for (int k = 0; k < UploadStage::SLOTS; k++) {
+        VDF_CUDA_CHECK(cudaHostAlloc((void**)&u.pinned[t][k], UploadStage::CHUNK, cudaHostAllocDefault));
+        VDF_CUDA_CHECK(cudaEventCreateWithFlags(&u.ev[t][k], cudaEventDisableTiming));
+      }
+    u.ready = true;
+  }
+  // copies run on the copy stream (the caller's stream may still be busy with the previous call's kernels, which
+  // read the same staging destination: order the copy stream behind them first), and the caller's stream waits for
+  // the last chunk
+  VDF_CUDA_CHECK(cudaEventRecord(c.start_ev, st));
+  VDF_CUDA_CHECK(cudaStreamWaitEvent(c.copy_stream, c.start_ev, 0));
+  const size_t chunks = (bytes + UploadStage::CHUNK - 1) / UploadStage::CHUNK;
+  const int device = c.device;
+  std::string errors[UploadStage::THREADS];
+  std::vector<std::thread> th;
+  for (int t = 0; t < UploadStage::THREADS; t++)
+    th.emplace_back([&, t] {
+      try {
+        VDF_CUDA_CHECK(cudaSetDevice(device));
+        int slot = 0;
+        for (size_t k = (size_t)t; k < chunks; k += UploadStage::THREADS, slot ^= 1) {
+          const size_t off = k * UploadStage::CHUNK, len = off + UploadStage::CHUNK <= bytes ? UploadStage::CHUNK : bytes - off;
+          if (u.used[t][slot]) VDF_CUDA_CHECK(cudaEventSynchronize(u.ev[t][slot]));   // its previous copy has drained
+          std::memcpy(u.pinned[t][slot], reinterpret_cast<const uint8_t*>(src) + off, len);
+          VDF_CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(dst) + off, u.pinned[t][slot], len, cudaMemcpyHostToDevice,
+                                         c.copy_stream));
+          VDF_CUDA_CHECK(cudaEventRecord(u.ev[t][slot], c.copy_stream));
+          u.used[t][slot] = true;
+        }
+      } catch (const std::exception& e) {
+        errors[t] = e.what();
+      }
+    });
+  for (auto& x : th) x.join();
+  for (auto& e : errors)
+    if (!e.empty()) throw std::runtime_error("staged upload: " + e);
+  VDF_CUDA_CHECK(cudaEventRecord(c.chunk_ev[0], c.copy_stream));
+  VDF_CUDA_CHECK(cudaStreamWaitEvent(st, c.chunk_ev[0], 0));
 }
 
 // ---- workspaces --------------------------------------------------------------------------------------
@@ -687,6 +749,14 @@ int vdfgpu_shutdown(void) {
     trim_locked();
     if (c.own_stream) cudaStreamDestroy(c.own_stream);
     if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
+    if (c.upload.ready) {
+      for (int t = 0; t < UploadStage::THREADS; t++)
+        for (int k = 0; k < UploadStage::SLOTS; k++) {
+          cudaFreeHost(c.upload.pinned[t][k]);
+          cudaEventDestroy(c.upload.ev[t][k]);
+        }
+      c.upload = UploadStage();
+    }
     for (auto& e : c.chunk_ev) { if (e) cudaEventDestroy(e); e = nullptr; }
     if (c.start_ev) cudaEventDestroy(c.start_ev);
     c.start_ev = nullptr;
@@ -872,7 +942,7 @@ int vdfgpu_msm(vdfgpu_gens* g, const void* scalars32_host, size_t n, void* out_p
       // persistent staging buffers of this stream: stable pointers, so a Nova-size commitment replays as a graph
       cudaStream_t st = cur_stream();
       Workspace* ws = staging_for(st, n);
-      h2d(ws->stage_sc, scalars32_host, n * 32, st);
+      h2d_scalars(ws->stage_sc, scalars32_host, n * 32, st);
       const bool hn = host_normalise_wanted(g);
       msm_on_device(g, 0, ws->stage_sc, n, ws->stage_out, true, nullptr, hn);
       d2h(out_point96_host, ws->stage_out, sizeof(jac_t), st);
@@ -1174,7 +1244,7 @@ static void mult_pippenger_body(int curve, void* out, const void* points, size_t
   if (workspaces_enabled()) {
     if (vdfgpu_gens* cached = dropin_lookup(curve, points, npoints)) {
       Workspace* ws = staging_for(st, npoints);
-      h2d(ws->stage_sc, scalars, npoints * 32, st);
+      h2d_scalars(ws->stage_sc, scalars, npoints * 32, st);
       const bool hn = host_normalise_wanted(cached);
       msm_on_device(cached, 0, ws->stage_sc, npoints, ws->stage_out, is_mont, nullptr, hn);
       d2h(out, ws->stage_out, sizeof(jac_t), st);
