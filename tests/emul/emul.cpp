@@ -92,7 +92,8 @@ MsmPlan plan_for(size_t n, size_t stride, int table, uint32_t c, uint32_t S, uin
   p.raw_jacobian = 0;
   p.affine_rounds = g_affine_rounds;
   p.affine_K = g_affine_K;
-  p.rec_warp = g_rec_warp;
+  p.rec_warp = g_rec_warp ? 1u : 0u;
+  p.rec_bucket = g_rec_warp == 2 ? 1u : 0u;   // 2: per-bucket record reduction (RecBucketFn)
   return p;
 }
 

@@ -87,10 +87,11 @@ def test_msm_skewed_and_edges(emul):
         for c, S, G in ((6, 4, 4), (9, 8, 5)):   # tiny S: > 4096 records -> record levels run
             assert _msm(emul, 0, table, c, S, G, 2, pts, sc) == want
     try:   # record levels in groups of 32 records (host mirror of the warp-cooperative level)
-        emul.emul_set_recwarp(1)
-        for table in (0, 1):
-            for c, S in ((6, 4), (9, 2), (4, 3)):
-                assert _msm(emul, 0, table, c, S, 4, 2, pts, sc) == want
+        for mode in (1, 2):    # 2: per-bucket record reduction (RecBucketFn, opt-in in the product)
+            emul.emul_set_recwarp(mode)
+            for table in (0, 1):
+                for c, S in ((6, 4), (9, 2), (4, 3)):
+                    assert _msm(emul, 0, table, c, S, 4, 2, pts, sc) == want
     finally:
         emul.emul_set_recwarp(0)
     assert _msm(emul, 0, 0, 8, 16, 4, 3, [], []) == bytes(96)

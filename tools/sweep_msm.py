@@ -15,6 +15,7 @@ from vdf_b200 import _lib, msm as G  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--log2n", type=int, nargs="+", default=[16, 18, 20, 22])
+ap.add_argument("--n", type=int, nargs="+", default=[], help="explicit point counts (instead of --log2n)")
 ap.add_argument("--layouts", nargs="+", default=["table", "plain"])
 ap.add_argument("--S", type=int, nargs="+", default=[0])
 ap.add_argument("--c", type=int, nargs="+", default=[0])
@@ -29,8 +30,8 @@ _stream = torch.cuda.Stream()
 torch.cuda.set_stream(_stream)
 _lib.check(lib.vdfgpu_set_stream(_stream.cuda_stream))
 names = ["digits", "scan", "scatter", "accumulate", "records", "reduce", "final"]
-for lg in args.log2n:
-    n = 1 << lg
+for n in (args.n or [1 << lg for lg in args.log2n]):
+    lg = n.bit_length() - 1
     scal = torch.randint(-(1 << 63), (1 << 63) - 1, (n, 4), dtype=torch.int64, device="cuda")
     scal[:, 3] &= (1 << 62) - 1
     out = torch.zeros(96, dtype=torch.uint8, device="cuda")
@@ -63,7 +64,7 @@ for lg in args.log2n:
                 buf = (ctypes.c_double * 7)()
                 _lib.check(lib.vdfgpu_profile_read(buf, 7))
                 _lib.check(lib.vdfgpu_profile_enable(0))
-                rec = {"log2n": lg, "layout": layout, "c": g.window_bits(n), "S": S, "affine": g.affine_rounds(n) if A < 0 else A, "K": K, "out": bytes(out.cpu().numpy()[:8]).hex(), "ms": round(total, 4),
+                rec = {"n": n, "log2n": lg, "layout": layout, "c": g.window_bits(n), "S": S, "affine": g.affine_rounds(n) if A < 0 else A, "K": K, "out": bytes(out.cpu().numpy()[:8]).hex(), "ms": round(total, 4),
                        "Gpts/s": round(n / total / 1e6, 4), "stages": {k: round(v, 4) for k, v in zip(names, buf)}}
                 print(json.dumps(rec), flush=True)
             g.close()

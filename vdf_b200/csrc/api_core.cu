@@ -371,6 +371,7 @@ static MsmPlan make_plan(const vdfgpu_gens* g, size_t n, bool is_mont, uint32_t 
   p.G = (uint32_t)env_long("VDFGPU_MSM_G", 16, 4, 1024);
   p.logm = (uint32_t)env_long("VDFGPU_MSM_LOGM", 3, 1, 8);
   p.rec_warp = (uint32_t)env_long("VDFGPU_MSM_RECWARP", 1, 0, 1);
+  p.rec_bucket = (uint32_t)env_long("VDFGPU_MSM_RECBUCKET", 0, 0, 1);
   // batched-affine halving rounds (msm_affine.cuh): worth their fixed costs only in the throughput regime and
   // while the buckets still hold >= 12 entries on average
   p.affine_rounds = 0;
@@ -445,7 +446,7 @@ static void msm_dispatch(vdfgpu_gens* g, const MsmPlan& p, Workspace* w, cudaStr
     return;
   }
   std::vector<uint64_t> key = {(uint64_t)g->curve, p.n, p.c, p.W, p.B, p.NB, p.table, p.level_stride, p.S, p.G, p.logm, p.is_mont, p.batch,
-                               p.len[0], p.len[1], p.len[2], p.len[3], p.raw_jacobian, p.rec_warp, p.affine_rounds, p.affine_K};
+                               p.len[0], p.len[1], p.len[2], p.len[3], p.raw_jacobian, p.rec_warp, p.rec_bucket, p.affine_rounds, p.affine_K};
   for (uint32_t j = 0; j < MSM_MAX_BATCH; j++) key.push_back((uint64_t)(uintptr_t)ss.v[j]);
   key.push_back((uint64_t)(uintptr_t)pts);
   key.push_back((uint64_t)(uintptr_t)d_out);

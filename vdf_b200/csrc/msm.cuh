@@ -50,11 +50,14 @@ struct MsmPlan {
   uint32_t len[4] = {0, 0, 0, 0};  // length of each vector (<= n); shorter vectors are zero-padded
   uint32_t raw_jacobian = 0;       // 1: write (X*ZZ, Y*ZZZ, ZZ) without the final inversion (caller normalises)
   uint32_t rec_warp = 0;           // 1: record levels by warp-cooperative segmented sums (RecWarpLevelFn)
+  uint32_t rec_bucket = 0;         // 1: small bucket sets reduce their boundary records per bucket (RecBucketFn; off: see there)
   uint32_t affine_rounds = 0;      // batched-affine halving rounds before the XYZZ accumulation (msm_affine.cuh)
   uint32_t affine_K = 64;          // additions per thread and round sharing one running product
 };
 
 constexpr uint32_t MSM_MAX_BATCH = 4;
+
+constexpr uint32_t MSM_REC_BUCKET_MAX = 32768;   // bucket sets up to this size reduce their records per bucket (RecBucketFn)
 
 #ifndef VDF_ACC_MINB
 #define VDF_ACC_MINB 5   // resident blocks per SM the XYZZ accumulation kernel is compiled for (96 registers)
@@ -417,6 +420,93 @@ struct RecOwnerFn {
   }
 };
 
+// Latency-regime alternative to the record levels: ONE launch, one warp per bucket.  The pieces of bucket b sit at
+// known slots of the record array -- range thread t covers list positions [t*S, (t+1)*S), so b = [bs, be) was cut by
+// threads t0 = bs/S .. t1 = (be-1)/S; t0's piece is in slot 2*t0 (+1 if b starts inside its range), every later
+// thread's in slot 2*t -- so lane j adds pieces j, j+32, ..., a shuffle tree adds the lanes, lane 0 stores the bucket.
+// A bucket that lies inside one range was stored by AccumulateFn itself.  Replaces 3-5 dependent launches
+// (RecWarpLevelFn / RecLevelFn / RecOwnerFn) when there are few buckets.
+// OFF BY DEFAULT (VDFGPU_MSM_RECBUCKET=1 enables it; measured in round 2, profiles/r2_experiments.md): with uniform
+// digits it cuts the records stage from 0.095 to 0.041 ms at 2^14 points (c = 13) and 0.134 to 0.113 ms at 75 344
+// (c = 15), but real inputs have HEAVY buckets -- the few digits of a narrow top window (c = 12, 14: three buckets of
+// n/4 entries), the many 0/1 values of a Nova witness -- whose hundreds of pieces a group (or even a whole warp, one
+// heavy bucket after the other) chains serially: 0.124 -> 0.19-0.26 ms at 13 904 points.  The record levels are
+// log-depth whatever the distribution.
+template <class C>
+struct RecBucketFn {
+  static constexpr uint32_t LANES = 8;   // lanes per bucket: a bucket of the latency regime has ~5-10 pieces
+  static constexpr uint32_t HEAVY = 24;  // more pieces than this: the whole warp sums the bucket
+  const uint32_t* offs;  // [NBK + 1] of the list AccumulateFn ran over
+  uint32_t NBK, S;
+  const xyzz_t* rec_pt;
+  xyzz_t* buckets;
+  VDF_HD void operator()(size_t idx) const {
+    const uint32_t b = (uint32_t)(idx / LANES);
+    uint32_t pieces = 0, t0 = 0, first_slot = 0;
+    if (b < NBK) {
+      const uint32_t bs = offs[b], be = offs[b + 1];
+      if (be > bs) {
+        t0 = bs / S;
+        const uint32_t t1 = (be - 1) / S;
+        if (t1 != t0) {
+          pieces = t1 - t0 + 1;
+          first_slot = 2 * t0 + (bs == t0 * S ? 0u : 1u);
+        }
+      }
+    }
+#if defined(__CUDA_ARCH__)
+    const unsigned sub = (unsigned)idx & (LANES - 1), lane = (unsigned)idx & 31u, full = 0xffffffffu;
+    // Heavy buckets (the top window's few digits, a witness's many 1s: hundreds of pieces) are summed by the WHOLE
+    // warp, one after the other; the group's own 8 lanes would chain pieces / 8 additions.
+    const bool heavy = pieces > HEAVY;
+    unsigned heavy_groups = __ballot_sync(full, heavy && sub == 0);
+    while (heavy_groups) {
+      const int src = __ffs(heavy_groups) - 1;   // lane 0 of the heavy group
+      heavy_groups &= heavy_groups - 1;
+      const uint32_t hp = __shfl_sync(full, pieces, src), ht0 = __shfl_sync(full, t0, src), hfs = __shfl_sync(full, first_slot, src);
+      const uint32_t hb = __shfl_sync(full, b, src);
+      xyzz_t h = C::identity();
+      for (uint32_t k = lane; k < hp; k += 32) C::add(h, rec_pt[k ? 2 * (size_t)(ht0 + k) : hfs]);
+#pragma unroll 1
+      for (int d = 16; d >= 1; d >>= 1) {
+        xyzz_t o;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          o.X.v[q] = __shfl_down_sync(full, h.X.v[q], d);
+          o.Y.v[q] = __shfl_down_sync(full, h.Y.v[q], d);
+          o.ZZ.v[q] = __shfl_down_sync(full, h.ZZ.v[q], d);
+          o.ZZZ.v[q] = __shfl_down_sync(full, h.ZZZ.v[q], d);
+        }
+        if (lane < (unsigned)d) C::add(h, o);
+      }
+      if (lane == 0) buckets[hb] = h;
+    }
+    const uint32_t light = heavy ? 0u : pieces;
+    xyzz_t v = C::identity();
+    for (uint32_t k = sub; k < light; k += LANES) C::add(v, rec_pt[k ? 2 * (size_t)(t0 + k) : first_slot]);
+#pragma unroll 1
+    for (int d = LANES / 2; d >= 1; d >>= 1) {
+      // all 32 lanes shuffle (four buckets per warp); a group whose bucket has no piece above lane d adds nothing
+      xyzz_t o;
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        o.X.v[q] = __shfl_down_sync(full, v.X.v[q], d, LANES);
+        o.Y.v[q] = __shfl_down_sync(full, v.Y.v[q], d, LANES);
+        o.ZZ.v[q] = __shfl_down_sync(full, v.ZZ.v[q], d, LANES);
+        o.ZZZ.v[q] = __shfl_down_sync(full, v.ZZZ.v[q], d, LANES);
+      }
+      if (sub < (unsigned)d && (uint32_t)d < light) C::add(v, o);
+    }
+    if (sub == 0 && light) buckets[b] = v;
+#else
+    if (idx % LANES || !pieces) return;
+    xyzz_t v = C::identity();
+    for (uint32_t k = 0; k < pieces; k++) C::add(v, rec_pt[k ? 2 * (size_t)(t0 + k) : first_slot]);
+    buckets[b] = v;
+#endif
+  }
+};
+
 // ---- stage 6: bucket reduction ---------------------------------------------------------------------
 // in: [NB][in_stride] points, first cnt of each row used, element j has weight j+1.
 // Thread (set, t) handles chunk [t*m, min((t+1)*m, cnt)):
@@ -485,6 +575,50 @@ struct BitScaleFn {
     xyzz_t acc = b < nbits ? bitsum[((size_t)set * nbits + b) * stride] : arr[(size_t)set * B + (B - 1)];
     for (uint32_t k = 0; k < b; k++) acc = C::dbl(acc);
     out[idx] = acc;
+  }
+};
+
+// BitScaleFn and the sum of its <= 32 terms in ONE launch: one warp per set, lane b scales its term by b doublings,
+// a shuffle tree adds the lanes.  Index = set * 32 + lane; launched with whole warps.
+template <class C>
+struct BitScaleSumFn {
+  const xyzz_t* bitsum;   // [sets * nbits][stride], element 0 of each row is S_b
+  size_t stride;
+  const xyzz_t* arr;      // [sets][B]
+  uint32_t B, nbits;      // nbits + 1 <= 32
+  xyzz_t* out;            // [sets]
+  VDF_HD void operator()(size_t idx) const {
+    const uint32_t set = (uint32_t)(idx >> 5);
+#if defined(__CUDA_ARCH__)
+    const unsigned lane = (unsigned)idx & 31u, full = 0xffffffffu;
+    xyzz_t v = C::identity();
+    if (lane <= nbits) {
+      v = lane < nbits ? bitsum[((size_t)set * nbits + lane) * stride] : arr[(size_t)set * B + (B - 1)];
+      for (uint32_t k = 0; k < lane; k++) v = C::dbl(v);
+    }
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+      xyzz_t o;
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        o.X.v[q] = __shfl_down_sync(full, v.X.v[q], d);
+        o.Y.v[q] = __shfl_down_sync(full, v.Y.v[q], d);
+        o.ZZ.v[q] = __shfl_down_sync(full, v.ZZ.v[q], d);
+        o.ZZZ.v[q] = __shfl_down_sync(full, v.ZZZ.v[q], d);
+      }
+      if (lane < (unsigned)d && (uint32_t)d <= nbits) C::add(v, o);
+    }
+    if (lane == 0) out[set] = v;
+#else
+    if (idx & 31) return;
+    xyzz_t acc = C::identity();
+    for (uint32_t b = 0; b <= nbits; b++) {
+      xyzz_t t = b < nbits ? bitsum[((size_t)set * nbits + b) * stride] : arr[(size_t)set * B + (B - 1)];
+      for (uint32_t k = 0; k < b; k++) t = C::dbl(t);
+      C::add(acc, t);
+    }
+    out[set] = acc;
+#endif
   }
 };
 
@@ -599,6 +733,10 @@ template <class L, class C>
 void msm_bit_combine(L& L_, uint32_t NBT, const xyzz_t* bitsum, size_t stride, const xyzz_t* arr, uint32_t B,
                      uint32_t nbits, xyzz_t* out) {
   const uint32_t per = nbits + 1;
+  if (per <= 32) {   // one launch: scale and sum in a warp per set
+    L_.template run<32>((size_t)NBT * 32, BitScaleSumFn<C>{bitsum, stride, arr, B, nbits, out});
+    return;
+  }
   xyzz_t* terms = L_.template alloc<xyzz_t>((size_t)NBT * per);
   xyzz_t* t1 = L_.template alloc<xyzz_t>((size_t)NBT * ((per + 3) / 4));
   L_.template run<32>((size_t)NBT * per, BitScaleFn<C>{bitsum, stride, arr, B, nbits, terms});
@@ -766,12 +904,20 @@ void msm_accumulate(L& L_, const MsmPlan& p, const affine_t* pts, const ScalarSe
                                                          hdr_a, pt_a, S});
   else
     L_.template run<128, VDF_ACC_MINB>(T_acc, AccumulateFn<C>{offs, NBK, sref, pts, nullptr, nullptr, buckets, hdr_a, pt_a, S});
-  L_.free(alist_x); L_.free(alist_offs);
-
   // segmented reduction of the records: log-depth levels, then owners
   RecHdr* hdr_b = nullptr;
   xyzz_t* pt_b = nullptr;
   L_.mark(MSM_STAGE_RECORDS);
+  if (p.rec_warp && p.rec_bucket && NBK <= MSM_REC_BUCKET_MAX) {
+    // latency regime: one warp per bucket gathers its pieces straight from the record array
+    const size_t rb_threads = ((size_t)NBK * RecBucketFn<C>::LANES + 31) / 32 * 32;   // whole warps: every lane shuffles
+    L_.template run<128>(rb_threads, RecBucketFn<C>{p.affine_rounds ? alist_offs : offs, NBK, S, pt_a, buckets});
+    L_.free(alist_x); L_.free(alist_offs);
+    L_.free(keys); L_.free(rank); L_.free(count); L_.free(offs); L_.free(sref);
+    L_.free(hdr_a); L_.free(pt_a);
+    return;
+  }
+  L_.free(alist_x); L_.free(alist_offs);
   // Each level maps G records to <= 2 (needs G > 2 to shrink).  Large problems: G = p.G (work-efficient),
   // stop at 4096 records.  Small problems are latency-bound (every level is a serial chain of <= G point
   // additions, and the owner pass is serial in the number of pieces of the heaviest bucket): G = 8, run
