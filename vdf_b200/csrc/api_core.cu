@@ -97,7 +97,11 @@ static void normalise(uint8_t* p96, int curve) {
 }  // namespace hostfield
 
 struct PendingNorm { void* p; size_t count; int curve; };
+struct PendingCopy { void* dst; const void* src; size_t bytes; };
 static thread_local std::vector<PendingNorm> t_norms;
+static thread_local std::vector<PendingCopy> t_copies;
+
+void copy_after_sync(void* dst, const void* src, size_t bytes) { t_copies.push_back({dst, src, bytes}); }
 
 void normalise_after_sync(void* host_ptr, size_t count, int curve) { t_norms.push_back({host_ptr, count, curve}); }
 
@@ -108,14 +112,18 @@ bool host_normalise_wanted(const vdfgpu_gens* g) {
 void discard_pending_sync() {
   t_wait_ev = nullptr;
   t_norms.clear();
+  t_copies.clear();
 }
 
 void wait_pending_sync() {
   cudaEvent_t ev = t_wait_ev;
   t_wait_ev = nullptr;
   std::vector<PendingNorm> norms;
+  std::vector<PendingCopy> copies;
   norms.swap(t_norms);
+  copies.swap(t_copies);
   if (ev) VDF_CUDA_CHECK(cudaEventSynchronize(ev));
+  for (const PendingCopy& cp : copies) std::memcpy(cp.dst, cp.src, cp.bytes);
   for (const PendingNorm& n : norms)
     for (size_t k = 0; k < n.count; k++) hostfield::normalise(reinterpret_cast<uint8_t*>(n.p) + 96 * k, n.curve);
 }
@@ -614,6 +622,8 @@ static vdfgpu_gens* gens_alloc(int curve, size_t n, uint32_t flags, uint32_t win
   g->n = n;
   g->flags = flags;
   bool table = flags & VDFGPU_GENS_TABLE;
+  if (!window_bits) window_bits = (uint32_t)env_long("VDFGPU_WINDOW_BITS", 0, 0, 24);   // tuning knob; 0 = by size
+  if (window_bits == 1) window_bits = 2;
   g->c = window_bits ? window_bits : msm_pick_c(n, table);
   g->W = table ? msm_windows(g->c) : 1;
   void* p = nullptr;

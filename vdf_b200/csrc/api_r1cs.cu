@@ -30,6 +30,7 @@ struct vdfgpu_running {
   vdf::fe* T = nullptr;   // cross-term [cons]
   vdf::fe* r = nullptr;   // challenge
   vdf::jac_t* comm = nullptr;  // [2] comm_W2, comm_T
+  uint8_t* bounce = nullptr;   // pinned: both commitments come back with one asynchronous copy; [1 + io] staging of uX2 behind it
   bool have_running = false, have_fresh = false;
 };
 
@@ -295,7 +296,9 @@ int vdfgpu_running_create(const vdfgpu_r1cs* s, vdfgpu_gens* gens, vdfgpu_runnin
       VDF_CUDA_CHECK(cudaMalloc((void**)&f->uX2, io1 * 32));
       VDF_CUDA_CHECK(cudaMalloc((void**)&f->r, 32));
       VDF_CUDA_CHECK(cudaMalloc((void**)&f->comm, 2 * sizeof(jac_t)));
+      VDF_CUDA_CHECK(cudaHostAlloc((void**)&f->bounce, 2 * sizeof(jac_t) + io1 * sizeof(fe), cudaHostAllocDefault));
     } catch (...) {
+      if (f->bounce) cudaFreeHost(f->bounce);
       cudaFree(f->W); cudaFree(f->W2); cudaFree(f->E); cudaFree(f->T); cudaFree(f->uX); cudaFree(f->uX2);
       cudaFree(f->r); cudaFree(f->comm);
       delete f;
@@ -316,6 +319,7 @@ int vdfgpu_running_destroy(vdfgpu_running* f) {
     }
     f->shape->refs--;
     f->gens->refs--;
+    cudaFreeHost(f->bounce);
     cudaFree(f->W); cudaFree(f->W2); cudaFree(f->E); cudaFree(f->T); cudaFree(f->uX); cudaFree(f->uX2);
     cudaFree(f->r); cudaFree(f->comm);
     delete f;
@@ -353,6 +357,16 @@ int vdfgpu_running_get(const vdfgpu_running* f, void* W_host, void* E_host, void
   });
 }
 
+// uX2 = [1 | X2] in one copy from the instance's pinned staging area (the previous step's copy has long completed:
+// every commit ends with a wait)
+static void upload_ux2(vdfgpu_running* f, const void* X2_host, cudaStream_t st) {
+  const vdfgpu_r1cs* s = f->shape;
+  fe* stage = reinterpret_cast<fe*>(f->bounce + 2 * sizeof(jac_t));
+  stage[0] = host_one(s->field);
+  if (s->io) std::memcpy(stage + 1, X2_host, (size_t)s->io * 32);
+  h2d(f->uX2, stage, (1 + (size_t)s->io) * 32, st);
+}
+
 // the part of running_commit after W2 / X2 are in place: T, then commit(W2) and commit(T) in one batched pass
 static void running_commit_enqueue(vdfgpu_running* f, void* comm_W2_point96_host, void* comm_T_point96_host) {
   Context& c = ctx();
@@ -365,9 +379,10 @@ static void running_commit_enqueue(vdfgpu_running* f, void* comm_W2_point96_host
   const size_t lens[2] = {s->vars, s->cons};
   const bool hn = host_normalise_wanted(f->gens);
   msm_batch_on_device(f->gens, vecs, lens, 2, f->comm, hn);
-  d2h(comm_W2_point96_host, f->comm, sizeof(jac_t), st);
-  d2h(comm_T_point96_host, f->comm + 1, sizeof(jac_t), st);
+  d2h(f->bounce, f->comm, 2 * sizeof(jac_t), st);      // pinned: asynchronous, waited for outside the lock
   sync_after_unlock(st);
+  copy_after_sync(comm_W2_point96_host, f->bounce, sizeof(jac_t));
+  copy_after_sync(comm_T_point96_host, f->bounce + sizeof(jac_t), sizeof(jac_t));
   if (hn) {
     normalise_after_sync(comm_W2_point96_host, 1, f->gens->curve);
     normalise_after_sync(comm_T_point96_host, 1, f->gens->curve);
@@ -384,10 +399,8 @@ int vdfgpu_running_commit(vdfgpu_running* f, const void* W2_host, const void* X2
     require_ready();
     cudaStream_t st = cur_stream();
     const vdfgpu_r1cs* s = f->shape;
-    fe one = host_one(s->field);
     h2d(f->W2, W2_host, (size_t)s->vars * 32, st);
-    h2d(f->uX2, &one, 32, st);
-    h2d(f->uX2 + 1, X2_host, (size_t)s->io * 32, st);
+    upload_ux2(f, X2_host, st);
     running_commit_enqueue(f, comm_W2_point96_host, comm_T_point96_host);
   });
 }
@@ -480,15 +493,13 @@ int vdfgpu_running_commit_step(vdfgpu_running* f, const vdfgpu_witness_bank* ban
     if (!f->have_running) throw StateError("running_commit_step: no running instance set");
     require_ready();
     cudaStream_t st = cur_stream();
-    fe one = host_one(s->field);
     const uint8_t* w2 = reinterpret_cast<const uint8_t*>(W2_host);
     // W2 = [ host part | 4t+1 step variables from the bank | host part ]: the step range never crosses PCIe
     h2d(f->W2, w2, step_offset * 32, st);
     h2d(f->W2 + step_offset + per, w2 + (step_offset + per) * 32, (nv - step_offset - per) * 32, st);
     VDF_CUDA_CHECK(cudaStreamWaitEvent(st, bank->ready, 0));
     d2d(f->W2 + step_offset, bank->w + step * per, per * 32, st);
-    h2d(f->uX2, &one, 32, st);
-    h2d(f->uX2 + 1, X2_host, (size_t)s->io * 32, st);
+    upload_ux2(f, X2_host, st);
     running_commit_enqueue(f, comm_W2_point96_host, comm_T_point96_host);
   });
 }

@@ -223,5 +223,8 @@ void msm_batch_on_device(vdfgpu_gens* g, const fe* const* d_scalars, const size_
 // split as the north star's: what cannot be parallelised stays on the host; Rust's to_affine() does this inversion on
 // the host for pasta-msm's results today.)  `count` consecutive 96-byte points at host_ptr, after the pending wait.
 void normalise_after_sync(void* host_ptr, size_t count, int curve);
+// after the pending wait, before the normalisations: memcpy(dst, src, bytes) -- results land in a pinned bounce buffer
+// with ONE asynchronous copy and are handed to the caller's (usually pageable) pointers on the host
+void copy_after_sync(void* dst, const void* src, size_t bytes);
 bool host_normalise_wanted(const vdfgpu_gens* g);
 }
