@@ -507,7 +507,28 @@ def sumcheck_measurements(lib, _lib, torch, ell=24):
     _lib.check(lib.vdfgpu_sumcheck_quad_dev(1, quad[0].data_ptr(), quad[1].data_ptr(), ell, ctypes.cast(fn, ctypes.c_void_p), None, final))
     dq = time.perf_counter() - t0
     algq = sum(2 * 32 * (n >> k) * 2 + 2 * 32 * (n >> (k + 1)) for k in range(ell))
-    return {"ell": ell, "entries": n, "rounds_called_back": len(calls) // (reps + 2),
+    # one IPA round's generator fold (CommitGens::fold): 2^16 outputs of r^-1 G_L + r G_R through the host API
+    ipa = {}
+    try:
+        import numpy as np
+        from vdf_b200 import msm as G
+        m = 1 << 16
+        g = G.Generators.progression(0, K0, D, 2 * m, table=False)
+        pts = np.zeros(72 * 2 * m, dtype=np.uint8)
+        _lib.check(lib.vdfgpu_gens_export(g._h, 0, 2 * m, pts.ctypes.data))
+        g.close()
+        w = np.frombuffer(os.urandom(64), dtype=np.uint8).copy()
+        w[31] &= 0x3F; w[63] &= 0x3F
+        outp = np.zeros(72 * m, dtype=np.uint8)
+        for _ in range(2):
+            t0 = time.perf_counter()
+            _lib.check(lib.vdfgpu_points_lincomb(0, pts.ctypes.data, pts.ctypes.data + 72 * m, m, w.ctypes.data, w.ctypes.data + 32, outp.ctypes.data))
+            di = time.perf_counter() - t0
+        ipa = {"outputs": m, "ms": di * 1e3, "outputs_per_s": m / di,
+               "note": "vdfgpu_points_lincomb, host points in and out (9.4 MB up, 4.7 MB down), two 255-bit scalars per output"}
+    except Exception as e:
+        ipa = {"error": repr(e)}
+    return {"ell": ell, "entries": n, "rounds_called_back": len(calls) // (reps + 2), "ipa_generator_fold": ipa,
             "cubic": {"ms": dt * 1e3, "algorithmic_bytes": alg, "achieved_gbs": alg / dt / 1e9, "frac_of_hbm": alg / dt / 1e9 / peak,
                       "field_mul_per_s": 10 * n / dt},
             "quad": {"ms": dq * 1e3, "algorithmic_bytes": algq, "achieved_gbs": algq / dq / 1e9, "frac_of_hbm": algq / dq / 1e9 / peak},

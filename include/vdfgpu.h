@@ -221,6 +221,16 @@ int vdfgpu_sumcheck_quad_dev(int field, void* A_dev, void* B_dev, size_t ell, vd
                              void* final_evals2_host);
 int vdfgpu_poly_evaluate(int field, const void* poly_host, const void* r_host, size_t ell, void* out_host);
 int vdfgpu_poly_evaluate_dev(int field, const void* poly_dev, const void* r_host, size_t ell, void* out_host);
+/* One round of the inner-product argument behind spartan_with_ipa_pc's polynomial-commitment opening halves vectors
+ * and generators with the challenge r:  a' = r a_L + r^-1 a_R (vec_lincomb: out[i] = x a[i] + y b[i]),
+ * c = <a_L, b_R> (inner_product), G'_i = r^-1 G_L,i + r G_R,i (points_lincomb: out[i] = w1 P[i] + w2 Q[i], affine in,
+ * affine out -- CommitGens::fold, which nova computes as n/2 two-point vartime_multiscalar_muls).  The two MSMs of a
+ * round (L and R) go through vdfgpu_msm / mult_pippenger_*. */
+int vdfgpu_vec_lincomb(int field, const void* a_host, const void* b_host, size_t n, const void* x32_host,
+                       const void* y32_host, void* out_host);
+int vdfgpu_inner_product(int field, const void* a_host, const void* b_host, size_t n, void* out32_host);
+int vdfgpu_points_lincomb(int curve, const void* P_affine72_host, const void* Q_affine72_host, size_t n,
+                          const void* w1_32_host, const void* w2_32_host, void* out_affine72_host);
 
 /* ---- a8: batched MinRoot verification.  Replaces a loop of MinRootVDF::check (src/minroot.rs:369-371)
  * / Evaluation::verify (:424-426) over independent chains.  ok_out[k] = 1 iff

@@ -151,6 +151,13 @@ extern "C" {
     pub fn vdfgpu_poly_evaluate_dev(field: c_int, poly_dev: *const c_void, r_host: *const c_void, ell: size_t,
                                     out_host: *mut c_void) -> c_int;
 
+    pub fn vdfgpu_vec_lincomb(field: c_int, a_host: *const c_void, b_host: *const c_void, n: size_t, x32_host: *const c_void,
+                              y32_host: *const c_void, out_host: *mut c_void) -> c_int;
+    pub fn vdfgpu_inner_product(field: c_int, a_host: *const c_void, b_host: *const c_void, n: size_t,
+                                out32_host: *mut c_void) -> c_int;
+    pub fn vdfgpu_points_lincomb(curve: c_int, p_affine72_host: *const c_void, q_affine72_host: *const c_void, n: size_t,
+                                 w1_32_host: *const c_void, w2_32_host: *const c_void, out_affine72_host: *mut c_void) -> c_int;
+
     // ---- a8: batched MinRoot verification
     pub fn vdfgpu_minroot_check_batch(field: c_int, results_state96_host: *const c_void,
                                       originals_state96_host: *const c_void, t_each: *const u64, t_uniform: u64,

@@ -58,3 +58,40 @@ def test_sumcheck_callback_failure_and_arguments(gpu_lib):
         SP.sumcheck(O.FIELD_FQ, [[1, 2, 3]] * 2, lambda r, e: 1)
     # the library is usable afterwards
     assert SP.eq_evals(O.FIELD_FQ, [5]) == [(1 - 5) % m, 5]
+
+
+@pytest.mark.parametrize("cid", [O.CURVE_PALLAS, O.CURVE_VESTA])
+def test_ipa_round_building_blocks(gpu_lib, cid):
+    """One round of the inner-product argument (CommitGens::fold, the vector folds, the cross inner products) against
+    Python integers, including identity generators, equal points (doubling inside P + Q) and P = -Q."""
+    cv = O.CURVES[cid]
+    fid = 1 if cid == 0 else 0          # scalar field of the curve
+    m = cv.order
+    py = random.Random(40 + cid)
+    n = 37
+    gens = [cv.mul(py.randrange(1, m), cv.gen) for _ in range(2 * n)]
+    gens[3] = None                       # identity on the left
+    gens[n + 5] = None                   # identity on the right
+    gens[n + 7] = gens[7]                # P == Q
+    gens[n + 9] = cv.neg(gens[9])        # P == -Q
+    r = py.randrange(1, m)
+    r_inv = pow(r, -1, m)
+    L, R = gens[:n], gens[n:]
+    got = SP.points_lincomb(cid, O.affines_to_bytes(cv, L), O.affines_to_bytes(cv, R), r_inv, r)
+    want = [cv.add(cv.mul(r_inv, a), cv.mul(r, b)) for a, b in zip(L, R)]
+    assert [O.affine_from_bytes(cv, got[72 * i:72 * i + 72]) for i in range(n)] == want
+    # folding preserves the commitment: <a', G'> = r^-1... check the algebra the IPA relies on
+    a = [py.randrange(m) for _ in range(2 * n)]
+    b = [py.randrange(m) for _ in range(2 * n)]
+    a2 = SP.vec_lincomb(fid, a[:n], a[n:], r, r_inv)
+    b2 = SP.vec_lincomb(fid, b[:n], b[n:], r_inv, r)
+    assert a2 == [(r * x + r_inv * y) % m for x, y in zip(a[:n], a[n:])]
+    cL, cR = SP.inner_product(fid, a[:n], b[n:]), SP.inner_product(fid, a[n:], b[:n])
+    assert cL == sum(x * y for x, y in zip(a[:n], b[n:])) % m
+    c = sum(x * y for x, y in zip(a, b)) % m
+    assert SP.inner_product(fid, a2, b2) == (c + r * r * cL + r_inv * r_inv * cR) % m
+    assert SP.inner_product(fid, [], []) == 0
+    # special scalars
+    assert SP.points_lincomb(cid, O.affines_to_bytes(cv, L[:4]), O.affines_to_bytes(cv, R[:4]), 0, 1) == O.affines_to_bytes(cv, R[:4])
+    assert SP.points_lincomb(cid, O.affines_to_bytes(cv, L[:4]), O.affines_to_bytes(cv, R[:4]), 1, 0) == O.affines_to_bytes(cv, L[:4])
+

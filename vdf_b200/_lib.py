@@ -79,6 +79,9 @@ PROTOTYPES = {
     "vdfgpu_sumcheck_quad_dev": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "vdfgpu_poly_evaluate": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vdfgpu_poly_evaluate_dev": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vdfgpu_vec_lincomb": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "vdfgpu_inner_product": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vdfgpu_points_lincomb": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "vdfgpu_minroot_check_batch": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_uint64, c_size_t, c_void_p]),
     "vdfgpu_minroot_check_batch_dev": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_uint64, c_size_t, c_void_p]),
     "vdfgpu_minroot_inverse_eval_batch": (c_int, [c_int, c_void_p, c_uint64, c_size_t, c_void_p]),

@@ -276,5 +276,75 @@ int vdfgpu_poly_evaluate(int field, const void* poly_host, const void* r_host, s
   return rc;
 }
 
+// ---- inner-product-argument building blocks ------------------------------------------------------------------
+int vdfgpu_vec_lincomb(int field, const void* a_host, const void* b_host, size_t n, const void* x32_host,
+                       const void* y32_host, void* out_host) {
+  return guarded([&] {
+    if (field != VDFGPU_FP && field != VDFGPU_FQ) throw ArgError("vec_lincomb: unknown field");
+    if (!x32_host || !y32_host || (n && (!a_host || !b_host || !out_host))) throw ArgError("vec_lincomb: null pointer");
+    if (!n) return;
+    require_ready();
+    cudaStream_t st = cur_stream();
+    CudaLaunch L(st);
+    DevBuf<fe> a(n, st), b(n, st), o(n, st), xy(2, st);
+    h2d(a.p, a_host, n * 32, st);
+    h2d(b.p, b_host, n * 32, st);
+    h2d(xy.p, x32_host, 32, st);
+    h2d(xy.p + 1, y32_host, 32, st);
+    if (field == VDFGPU_FP) L.run<256>(n, VecLinCombFn<Fp>{a.p, b.p, xy.p, o.p});
+    else L.run<256>(n, VecLinCombFn<Fq>{a.p, b.p, xy.p, o.p});
+    ctx().launches += L.launches;
+    d2h(out_host, o.p, n * 32, st);
+    sync_after_unlock(st);
+  });
+}
+
+int vdfgpu_inner_product(int field, const void* a_host, const void* b_host, size_t n, void* out32_host) {
+  return guarded([&] {
+    if (field != VDFGPU_FP && field != VDFGPU_FQ) throw ArgError("inner_product: unknown field");
+    if (!out32_host || (n && (!a_host || !b_host))) throw ArgError("inner_product: null pointer");
+    require_ready();
+    cudaStream_t st = cur_stream();
+    DevBuf<fe> a(n ? n : 1, st), b(n ? n : 1, st), partial((size_t)148 * 8, st), res(1, st);
+    h2d(a.p, a_host, n * 32, st);
+    h2d(b.p, b_host, n * 32, st);
+    ScScratch s;
+    s.partial = partial.p;
+    s.evals = res.p;
+    if (field == VDFGPU_FP) dot_enqueue<Fp>(st, a.p, b.p, n, s);
+    else dot_enqueue<Fq>(st, a.p, b.p, n, s);
+    d2h(out32_host, res.p, sizeof(fe), st);
+    sync_after_unlock(st);
+  });
+}
+
+int vdfgpu_points_lincomb(int curve, const void* P_affine72_host, const void* Q_affine72_host, size_t n,
+                          const void* w1_32_host, const void* w2_32_host, void* out_affine72_host) {
+  return guarded([&] {
+    if (curve != VDFGPU_PALLAS && curve != VDFGPU_VESTA) throw ArgError("points_lincomb: unknown curve");
+    if (!w1_32_host || !w2_32_host || (n && (!P_affine72_host || !Q_affine72_host || !out_affine72_host)))
+      throw ArgError("points_lincomb: null pointer");
+    if (!n) return;
+    require_ready();
+    cudaStream_t st = cur_stream();
+    CudaLaunch L(st);
+    DevBuf<uint8_t> raw(2 * n * 72, st);
+    DevBuf<affine_t> pq(2 * n, st), out(n, st);
+    DevBuf<fe> w(2, st);
+    h2d(raw.p, P_affine72_host, n * 72, st);
+    h2d(raw.p + n * 72, Q_affine72_host, n * 72, st);
+    h2d(w.p, w1_32_host, 32, st);
+    h2d(w.p + 1, w2_32_host, 32, st);
+    L.run<256>(2 * n, RepackFn{raw.p, pq.p});
+    const size_t threads = (n + 3) / 4;
+    if (curve == VDFGPU_PALLAS) L.run<64>(threads, PointLinCombFn<Pallas, Fp, Fq>{pq.p, pq.p + n, w.p, out.p, n});
+    else L.run<64>(threads, PointLinCombFn<Vesta, Fq, Fp>{pq.p, pq.p + n, w.p, out.p, n});
+    L.run<256>(n, UnpackFn{out.p, raw.p});
+    ctx().launches += L.launches;
+    d2h(out_affine72_host, raw.p, n * 72, st);
+    sync_after_unlock(st);
+  });
+}
+
 #pragma GCC visibility pop
 }  // extern "C"

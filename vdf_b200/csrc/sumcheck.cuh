@@ -16,10 +16,79 @@
 // Nova's own sizes (2^14 - 2^17 entries, L2-resident).  Reductions: per-thread strided partial sums, a shuffle tree
 // per warp, shared memory across the warps of a block, one partial per block, a second one-block launch.
 #pragma once
+#include "curve.cuh"
 #include "field.cuh"
 #include "launch.cuh"
 
 namespace vdf {
+
+// ---- inner-product-argument building blocks (the polynomial-commitment opening of spartan_with_ipa_pc, [R]) --------
+// One IPA round halves the vectors and the generators with the challenge r:
+//   a' = r a_L + r^-1 a_R,  b' = r^-1 b_L + r b_R              (VecLinCombFn: out[i] = x a[i] + y b[i])
+//   G'_i = r^-1 G_L,i + r G_R,i   (CommitGens::fold: n/2 independent two-term scalar multiplications;
+//                                  nova computes each with vartime_multiscalar_mul on two points)
+//   c_L = <a_L, b_R>, c_R = <a_R, b_L>                        (sc_dot_kernel below)
+template <class F>
+struct VecLinCombFn {
+  const fe* a; const fe* b; const fe* xy;   // xy[0] = x, xy[1] = y (Montgomery)
+  fe* out;
+  VDF_HD void operator()(size_t i) const {
+    fe_store(out + i, F::add(F::mul(fe_load(xy), fe_load(a + i)), F::mul(fe_load(xy + 1), fe_load(b + i))));
+  }
+};
+
+// out[i] = w1 P[i] + w2 Q[i] on packed affine points, normalised to affine again.  Thread = CH consecutive outputs:
+// each by interleaved double-and-add over the bits of both scalars (Shamir's trick: one doubling per bit, one addition
+// of P, Q or P + Q), then ONE inversion for the CH results (Montgomery's trick).  C = curve, SF = its scalar field.
+template <class C, class F, class SF>
+struct PointLinCombFn {
+  const affine_t* P; const affine_t* Q;
+  const fe* w;            // w[0] = w1, w[1] = w2 (Montgomery, scalar field)
+  affine_t* out;
+  size_t n;
+  static constexpr int CH = 4;
+  VDF_HD void operator()(size_t t) const {
+    const size_t lo = t * CH, hi = lo + CH < n ? lo + CH : n;
+    const fe k1 = SF::from_mont(fe_load(w)), k2 = SF::from_mont(fe_load(w + 1));
+    xyzz_t res[CH];
+    fe pref[CH];
+    fe run = F::one();
+    for (size_t i = lo; i < hi; i++) {
+      affine_t p, q;
+      p.x = fe_load(&P[i].x); p.y = fe_load(&P[i].y);
+      q.x = fe_load(&Q[i].x); q.y = fe_load(&Q[i].y);
+      xyzz_t pq = C::from_affine(p);
+      C::madd_signed(pq, q, false);                       // P + Q (identity operands and P = +-Q handled inside)
+      xyzz_t acc = C::identity();
+#pragma unroll 1
+      for (int bit = 255; bit >= 0; bit--) {
+        acc = C::dbl(acc);
+        const uint32_t b1 = (k1.v[bit >> 5] >> (bit & 31)) & 1u, b2 = (k2.v[bit >> 5] >> (bit & 31)) & 1u;
+        if (b1 & b2) C::add(acc, pq);
+        else if (b1) C::madd_signed(acc, p, false);
+        else if (b2) C::madd_signed(acc, q, false);
+      }
+      res[i - lo] = acc;
+      pref[i - lo] = run;
+      if (!C::is_inf(acc)) run = F::mul(run, F::mul(acc.ZZ, acc.ZZZ));
+    }
+    fe inv = F::inv(run);
+    for (size_t i = hi; i > lo; i--) {
+      const xyzz_t& r = res[i - 1 - lo];
+      affine_t a;
+      if (C::is_inf(r)) {
+        a.x = F::zero(); a.y = F::zero();
+      } else {
+        const fe zi = F::mul(inv, pref[i - 1 - lo]);        // 1 / (ZZ * ZZZ)
+        inv = F::mul(inv, F::mul(r.ZZ, r.ZZZ));
+        a.x = F::mul(r.X, F::mul(zi, r.ZZZ));
+        a.y = F::mul(r.Y, F::mul(zi, r.ZZ));
+      }
+      fe_store(&out[i - 1].x, a.x);
+      fe_store(&out[i - 1].y, a.y);
+    }
+  }
+};
 
 constexpr int SC_BLOCK = 256;
 constexpr int SC_MAX_POLYS = 4;

@@ -64,3 +64,38 @@ def sumcheck(field_id: int, tables: Sequence[Sequence[int]], challenge: Challeng
         rc = lib.vdfgpu_sumcheck_quad(field_id, *[_lib.as_ptr(b) for b in bufs], ell, cbp, None, _lib.as_ptr(final))
     _lib.check(rc)
     return [e for e, _ in log], [r for _, r in log], fes_from_bytes(bytes(final), m)
+
+
+# ---- inner-product-argument building blocks -----------------------------------------------------------------
+def vec_lincomb(field_id: int, a: Sequence[int], b: Sequence[int], x: int, y: int) -> List[int]:
+    """out[i] = x a[i] + y b[i] (the vector folds of one IPA round)."""
+    m = MODULUS[field_id]
+    if len(a) != len(b):
+        raise ValueError("vec_lincomb: length mismatch")
+    out = bytearray(32 * len(a))
+    _lib.check(_lib.load().vdfgpu_vec_lincomb(field_id, _lib.as_ptr(fes_to_bytes(a, m)), _lib.as_ptr(fes_to_bytes(b, m)), len(a),
+                                              _lib.as_ptr(fe_to_bytes(x, m)), _lib.as_ptr(fe_to_bytes(y, m)), _lib.as_ptr(out)))
+    return fes_from_bytes(bytes(out), m)
+
+
+def inner_product(field_id: int, a: Sequence[int], b: Sequence[int]) -> int:
+    m = MODULUS[field_id]
+    if len(a) != len(b):
+        raise ValueError("inner_product: length mismatch")
+    out = bytearray(32)
+    _lib.check(_lib.load().vdfgpu_inner_product(field_id, _lib.as_ptr(fes_to_bytes(a, m) or bytes(32)),
+                                                _lib.as_ptr(fes_to_bytes(b, m) or bytes(32)), len(a), _lib.as_ptr(out)))
+    return fe_from_bytes(bytes(out), m)
+
+
+def points_lincomb(curve: int, P: bytes, Q: bytes, w1: int, w2: int) -> bytes:
+    """out[i] = w1 P[i] + w2 Q[i] on 72-byte affine points (CommitGens::fold of one IPA round)."""
+    from .encoding import CURVE_ORDER
+    if len(P) != len(Q) or len(P) % 72:
+        raise ValueError("points_lincomb: two affine arrays of the same length")
+    order = CURVE_ORDER[curve]
+    out = bytearray(len(P))
+    _lib.check(_lib.load().vdfgpu_points_lincomb(curve, _lib.as_ptr(P), _lib.as_ptr(Q), len(P) // 72,
+                                                 _lib.as_ptr(fe_to_bytes(w1, order)), _lib.as_ptr(fe_to_bytes(w2, order)), _lib.as_ptr(out)))
+    return bytes(out)
+
