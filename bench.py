@@ -367,10 +367,6 @@ def nova_step_measurements(_lib, ts=(10, 100, 1000, 1024, 4096, 16384)):
             dt = timed(step)
             if not raw:
                 entry.update({"fold_steps_per_s": 1.0 / dt, "ms": dt * 1e3})
-                try:   # CPU restatement of the same step's data-parallel work on the host cores (oracle/cpu_ref.c, "port")
-                    entry["cpu_port"] = cpu_fold_step(shape, W, X, sec_shape, sec_W, sec_X, gens, sec_gens, _lib)
-                except Exception as e:
-                    entry["cpu_port"] = {"error": repr(e)}
             else:
                 entry.update({"raw_jacobian_fold_steps_per_s": 1.0 / dt, "raw_jacobian_ms": dt * 1e3})
                 # f1: the step part of the witness comes from the device-resident bank (one state per step; the bench
@@ -386,6 +382,12 @@ def nova_step_measurements(_lib, ts=(10, 100, 1000, 1024, 4096, 16384)):
                 dtb = timed(step_bank)
                 entry.update({"bank_fold_steps_per_s": 1.0 / dtb, "bank_ms": dtb * 1e3})
                 bank.close()
+                # CPU restatement of the same step's data-parallel work on the host cores (oracle/cpu_ref.c, "port");
+                # after every GPU variant: 16 busy host threads disturb the next wall-clock measurement for a while
+                try:
+                    entry["cpu_port"] = cpu_fold_step(shape, W, X, sec_shape, sec_W, sec_X, gens, sec_gens, _lib)
+                except Exception as e:
+                    entry["cpu_port"] = {"error": repr(e)}
             pri.close(); sec.close(); gens.close(); sec_gens.close()
         gs.close()
         res[str(t)] = entry

@@ -94,6 +94,35 @@ static void normalise(uint8_t* p96, int curve) {
   mul(Y, Y, zi3, f);
   std::memcpy(p96, X, 32); std::memcpy(p96 + 32, Y, 32); std::memcpy(p96 + 64, f.one, 32);
 }
+
+// the same for m <= 16 points with one inversion: 1 / (Z_0 ... Z_{m-1}), then the individual inverses by back-substitution
+static void normalise_batch(uint8_t* const* pts, size_t m, int curve) {
+  const Mod& f = curve == VDFGPU_PALLAS ? FP_MOD : FQ_MOD;
+  uint64_t Z[16][4], pre[16][4], run[4];
+  std::memcpy(run, f.one, 32);
+  for (size_t k = 0; k < m; k++) {
+    std::memcpy(Z[k], pts[k] + 64, 32);
+    std::memcpy(pre[k], run, 32);
+    if (Z[k][0] | Z[k][1] | Z[k][2] | Z[k][3]) mul(run, run, Z[k], f);
+  }
+  uint64_t inv_all[4];
+  inv(inv_all, run, f);
+  for (size_t k = m; k-- > 0;) {
+    if ((Z[k][0] | Z[k][1] | Z[k][2] | Z[k][3]) == 0) {
+      std::memset(pts[k], 0, 96);
+      continue;
+    }
+    uint64_t zi[4], zi2[4], zi3[4], X[4], Y[4];
+    mul(zi, inv_all, pre[k], f);
+    mul(inv_all, inv_all, Z[k], f);
+    std::memcpy(X, pts[k], 32); std::memcpy(Y, pts[k] + 32, 32);
+    mul(zi2, zi, zi, f);
+    mul(zi3, zi2, zi, f);
+    mul(X, X, zi2, f);
+    mul(Y, Y, zi3, f);
+    std::memcpy(pts[k], X, 32); std::memcpy(pts[k] + 32, Y, 32); std::memcpy(pts[k] + 64, f.one, 32);
+  }
+}
 }  // namespace hostfield
 
 struct PendingNorm { void* p; size_t count; int curve; };
@@ -124,8 +153,20 @@ void wait_pending_sync() {
   copies.swap(t_copies);
   if (ev) VDF_CUDA_CHECK(cudaEventSynchronize(ev));
   for (const PendingCopy& cp : copies) std::memcpy(cp.dst, cp.src, cp.bytes);
-  for (const PendingNorm& n : norms)
-    for (size_t k = 0; k < n.count; k++) hostfield::normalise(reinterpret_cast<uint8_t*>(n.p) + 96 * k, n.curve);
+  // all points of one call share ONE inversion per curve (Montgomery's trick): a fold step returns two commitments
+  for (int curve = 0; curve < 2; curve++) {
+    uint8_t* pts[16];
+    size_t m = 0;
+    for (const PendingNorm& n : norms)
+      for (size_t k = 0; k < n.count; k++) {
+        if (n.curve != curve) continue;
+        uint8_t* p = reinterpret_cast<uint8_t*>(n.p) + 96 * k;
+        if (m < 16) pts[m++] = p;
+        else hostfield::normalise(p, curve);
+      }
+    if (m == 1) hostfield::normalise(pts[0], curve);
+    else if (m > 1) hostfield::normalise_batch(pts, m, curve);
+  }
 }
 
 
@@ -1089,7 +1130,13 @@ int vdfgpu_point_normalise_host(int curve, void* points96_host, size_t count) {
     set_error("point_normalise_host: null pointer");
     return VDFGPU_ERR_ARG;
   }
-  for (size_t k = 0; k < count; k++) hostfield::normalise(reinterpret_cast<uint8_t*>(points96_host) + 96 * k, curve);
+  for (size_t k = 0; k < count;) {   // 16 points per inversion
+    uint8_t* pts[16];
+    size_t m = 0;
+    for (; m < 16 && k < count; m++, k++) pts[m] = reinterpret_cast<uint8_t*>(points96_host) + 96 * k;
+    if (m == 1) hostfield::normalise(pts[0], curve);
+    else hostfield::normalise_batch(pts, m, curve);
+  }
   return VDFGPU_OK;
 }
 
