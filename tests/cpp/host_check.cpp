@@ -87,9 +87,17 @@ int main(int argc, char** argv) {
       auto c = run.commit(W2, X2);
       bad += !(c.comm_T == commT);
       run.fold(r[0]);
-      std::vector<Fe> Wf(dims[1]), Ef(dims[0]), Xf(dims[2]);
+      std::vector<Fe> Wf, Ef, Xf;   // get() sizes its outputs (empty vectors used to overflow the heap)
       Fe uf{};
       run.get(Wf, Ef, uf, Xf);
+      bad += !(Wf.size() == dims[1] && Ef.size() == dims[0] && Xf.size() == dims[2]);
+      // nova-snark answers a wrong length with InvalidWitnessLength; the host layer must not let the C ABI read past it
+      auto throws = [](auto&& fn) { try { fn(); } catch (const std::invalid_argument&) { return 1; } return 0; };
+      std::vector<Fe> shortW(W2.begin(), W2.end() - 1);
+      bad += !throws([&] { run.commit(shortW, X2); });
+      bad += !throws([&] { run.set(shortW, E1, u1[0], X1); });
+      bad += !throws([&] { shape.commit_T(g, shortW, u1[0], X1, W2, X2); });
+      bad += !throws([&] { shape.multiply_vec(shortW); });
       auto wantW = as<Fe>(slurp(d + "r1cs_Wfold.bin")), wantE = as<Fe>(slurp(d + "r1cs_Efold.bin"));
       for (size_t k = 0; k < dims[1]; k++) bad += !(Wf[k] == wantW[k]);
       for (size_t k = 0; k < dims[0]; k++) bad += !(Ef[k] == wantE[k]);

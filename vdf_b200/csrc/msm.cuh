@@ -92,7 +92,7 @@ static inline uint32_t msm_pick_c(size_t n, bool table) {
   // buckets -- n/4 to n/2 entries each -- and those heavy buckets are cut into hundreds of boundary records whose
   // reduction is the longest dependent chain of a latency-regime MSM (measured: 13 904 points at c = 12 take 0.51 ms,
   // 16 384 points at c = 13 take 0.43 ms).  The next window size up has a healthy top window (7 or more bits, or none).
-  if (c == 11 || c == 12 || c == 14 || c == 18) c++;
+  while (c == 11 || c == 12 || c == 14 || c == 18) c++;
   return (uint32_t)c;
 }
 
