@@ -107,14 +107,18 @@ struct Curve {
   static xyzz_t dbl_affine_cold(const fe& x, const fe& y) { return dbl_affine(x, y); }
 #endif
 
+#ifndef VDF_MADD_MUL
+#define VDF_MADD_MUL mul_call
+#define VDF_MADD_SQR sqr_call
+#endif
   // madd with the multiplier called out of line (same arithmetic; used by the accumulate kernel)
   static VDF_HD void madd_call(xyzz_t& acc, const fe& x2, const fe& y2) {
     if (is_inf(acc)) {
       acc.X = x2; acc.Y = y2; acc.ZZ = F::one(); acc.ZZZ = F::one();
       return;
     }
-    fe U2 = F::mul_call(x2, acc.ZZ);
-    fe S2 = F::mul_call(y2, acc.ZZZ);
+    fe U2 = F::VDF_MADD_MUL(x2, acc.ZZ);
+    fe S2 = F::VDF_MADD_MUL(y2, acc.ZZZ);
     fe P = F::sub(U2, acc.X);
     fe R = F::sub(S2, acc.Y);
     if (F::is_zero(P)) {
@@ -122,13 +126,13 @@ struct Curve {
       else acc = identity();
       return;
     }
-    fe PP = F::sqr_call(P);
-    fe PPP = F::mul_call(P, PP);
-    fe Q = F::mul_call(acc.X, PP);
-    fe X3 = F::sub(F::sub(F::sqr_call(R), PPP), F::dbl(Q));
-    fe Y3 = F::sub(F::mul_call(R, F::sub(Q, X3)), F::mul_call(acc.Y, PPP));
-    acc.ZZ = F::mul_call(acc.ZZ, PP);
-    acc.ZZZ = F::mul_call(acc.ZZZ, PPP);
+    fe PP = F::VDF_MADD_SQR(P);
+    fe PPP = F::VDF_MADD_MUL(P, PP);
+    fe Q = F::VDF_MADD_MUL(acc.X, PP);
+    fe X3 = F::sub(F::sub(F::VDF_MADD_SQR(R), PPP), F::dbl(Q));
+    fe Y3 = F::sub(F::VDF_MADD_MUL(R, F::sub(Q, X3)), F::VDF_MADD_MUL(acc.Y, PPP));
+    acc.ZZ = F::VDF_MADD_MUL(acc.ZZ, PP);
+    acc.ZZZ = F::VDF_MADD_MUL(acc.ZZZ, PPP);
     acc.X = X3;
     acc.Y = Y3;
   }

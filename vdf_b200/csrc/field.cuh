@@ -508,7 +508,12 @@ struct Field {
 #if defined(__CUDACC__)
   static __device__ __noinline__ fe mul_call(const fe& a, const fe& b) { return mul(a, b); }
   static __device__ __noinline__ fe sqr_call(const fe& a) { return sqr(a); }
+  // operands and result in registers (by value): no trip through the local-memory stack around the call
+  static __device__ __noinline__ fe mul_val(fe a, fe b) { return mul(a, b); }
+  static __device__ __noinline__ fe sqr_val(fe a) { return sqr(a); }
 #else
+  static fe mul_val(fe a, fe b) { return mul(a, b); }
+  static fe sqr_val(fe a) { return sqr(a); }
   static fe mul_call(const fe& a, const fe& b) { return mul(a, b); }
   static fe sqr_call(const fe& a) { return sqr(a); }
 #endif

@@ -31,6 +31,7 @@
 #include "curve.cuh"
 #include "launch.cuh"
 #include "msm_affine.cuh"
+#include "quad.cuh"
 
 namespace vdf {
 
@@ -403,6 +404,126 @@ struct RecWarpLevelFn {
   }
 };
 
+// The record levels of the latency regime: one block takes 256 consecutive slots to <= 2 records.
+//
+// The records of a bucket are contiguous in the list, so after squeezing out the empty slots a bucket is a RUN of
+// equal keys.  Every record knows its rank inside its run; in round j the records of rank = 0 mod 2^(j+1) add the
+// record 2^j places to their right when it belongs to the same run.  All runs shrink together -- the chain is
+// log2(longest run of the block) additions, 3-4 with ~9 pieces per bucket, however many buckets the block holds (a
+// binary tree over the slots would add across one of its node boundaries at every one of its log2(256) levels, because
+// every boundary cuts some bucket).  Each addition is done by a quad (quad.cuh).  The run heads then hold the run
+// totals: a run with its bucket's first AND last piece is stored, the others -- at most the leftmost and the rightmost
+// run of the block -- go to the next level as records 2g and 2g+1.  Launched with a multiple of 256 threads.
+// (The CPU emulation runs the serial functor with G = 256: same outputs.)
+template <class C>
+struct RecRunsFn {
+  static constexpr uint32_t NS = 256;
+  const RecHdr* in_hdr;
+  const xyzz_t* in_pt;
+  size_t n_in;
+  xyzz_t* buckets;
+  RecHdr* out_hdr;  // [2 * blocks]
+  xyzz_t* out_pt;
+#if defined(__CUDA_ARCH__)
+  static __device__ __forceinline__ fe* comp(xyzz_t* p, unsigned r) {
+    return r == 0 ? &p->X : r == 1 ? &p->Y : r == 2 ? &p->ZZ : &p->ZZZ;
+  }
+#endif
+  VDF_HD void operator()(size_t idx) const {
+#if defined(__CUDA_ARCH__)
+    typedef Quad<typename C::field> Q;
+    __shared__ xyzz_t sp[NS];
+    __shared__ uint32_t ckey[NS + 1], cflg[NS], rnk[NS];
+    __shared__ uint32_t wtot[NS / 32], wmax[NS / 32], s_lo, s_hi, s_cnt;
+    __shared__ uint16_t wl[NS];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, full = 0xffffffffu;
+    const size_t g = idx >> 8, base = g * NS;
+    // squeeze out the empty slots (slot tid -> compact index p)
+    RecHdr h;
+    h.bucket = REC_NONE; h.flags = 0;
+    if (base + tid < n_in) h = in_hdr[base + tid];
+    const bool real = h.bucket != REC_NONE;
+    const unsigned bal = __ballot_sync(full, real);
+    if (lane == 0) wtot[warp] = __popc(bal);
+    if (tid == 0) { s_lo = 0xffffffffu; s_hi = 0u; }
+    __syncthreads();
+    unsigned off = 0, M = 0;
+#pragma unroll
+    for (unsigned w = 0; w < NS / 32; w++) {
+      if (w < warp) off += wtot[w];
+      M += wtot[w];
+    }
+    if (real) {
+      const unsigned p = off + __popc(bal & ((1u << lane) - 1u));
+      ckey[p] = h.bucket;
+      cflg[p] = h.flags;
+      sp[p] = in_pt[base + tid];
+    }
+    if (tid == 0) ckey[M] = REC_NONE;
+    __syncthreads();
+    // rank inside the run = p - (start of the run): running maximum of the head positions
+    {
+      const bool head = tid < M && (tid == 0 || ckey[tid - 1] != ckey[tid]);
+      unsigned v = head ? tid : 0u;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_up_sync(full, v, d);
+        if (lane >= (unsigned)d && o > v) v = o;
+      }
+      if (lane == 31) wmax[warp] = v;
+      __syncthreads();
+      for (unsigned w = 0; w < warp; w++) v = wmax[w] > v ? wmax[w] : v;
+      if (tid < M) rnk[tid] = tid - v;
+    }
+    __syncthreads();
+    // pairing rounds: the additions of a round are listed first, so that every quad gets its share of REAL work (the
+    // lanes of a warp would otherwise all wait through the additions of the quad that has the most candidates)
+    const unsigned q = tid >> 2, r = tid & 3u;
+#pragma unroll 1
+    for (unsigned st = 1; st < NS; st <<= 1) {
+      if (tid == 0) s_cnt = 0;
+      __syncthreads();
+      if (tid + st < M && (rnk[tid] & (2 * st - 1)) == 0 && ckey[tid + st] == ckey[tid]) wl[atomicAdd(&s_cnt, 1u)] = tid;
+      __syncthreads();
+      const unsigned cnt = s_cnt;
+      if (cnt == 0) break;
+#pragma unroll 1
+      for (unsigned i = q; i < cnt; i += NS / 4) {
+        const unsigned p = wl[i];
+        xyzz_t a = sp[p];
+        const xyzz_t o = sp[p + st];
+        __syncwarp(Q::mask());   // every lane of the quad has read both points before any lane overwrites one
+        Q::add(a, o);
+        fe_store(comp(&sp[p], r), Q::pick(r, a.X, a.Y, a.ZZ, a.ZZZ));
+        if (r == 0) cflg[p] |= cflg[p + st];
+      }
+      __syncthreads();
+    }
+    // run heads: finished buckets are stored, the (<= 2) others are the block's output
+    if (tid < M && rnk[tid] == 0) {
+      if ((cflg[tid] & REC_FIRST) && (cflg[tid] & REC_LAST)) {
+        buckets[ckey[tid]] = sp[tid];
+      } else {
+        atomicMin(&s_lo, tid);
+        atomicMax(&s_hi, tid);
+      }
+    }
+    __syncthreads();
+    if (tid < 2) {
+      const bool have = tid == 0 ? s_lo != 0xffffffffu : (s_lo != 0xffffffffu && s_hi != s_lo);
+      const unsigned p = tid == 0 ? s_lo : s_hi;
+      RecHdr o;
+      o.bucket = have ? ckey[p] : REC_NONE;
+      o.flags = have ? cflg[p] : 0u;
+      out_hdr[2 * g + tid] = o;
+      if (have) out_pt[2 * g + tid] = sp[p];
+    }
+#else
+    if ((idx & 255) == 0) RecLevelFn<C>{in_hdr, in_pt, n_in, buckets, out_hdr, out_pt, NS}(idx >> 8);
+#endif
+  }
+};
+
 // last level: the owner (record flagged REC_FIRST) folds the following records of its bucket
 template <class C>
 struct RecOwnerFn {
@@ -565,6 +686,28 @@ struct BitPairFn {
   }
 };
 
+// BitPairFn with one QUAD per output (quad.cuh): index = output * 4 + lane of the quad
+template <class C>
+struct BitPairQuadFn {
+  const xyzz_t* buckets;
+  uint32_t B, nbits;
+  xyzz_t* out;
+  VDF_HD void operator()(size_t idx) const {
+#if defined(__CUDA_ARCH__)
+    const size_t o = idx >> 2;
+    const uint32_t q4 = B / 4;
+    uint32_t row = (uint32_t)(o / q4), q = (uint32_t)(o - (size_t)row * q4);
+    uint32_t set = row / nbits, b = row - set * nbits;
+    const xyzz_t* bk = buckets + (size_t)set * B;
+    xyzz_t acc = bk[BitPairFn<C>::insert_bit(2 * q, b) - 1];
+    Quad<typename C::field>::add(acc, bk[BitPairFn<C>::insert_bit(2 * q + 1, b) - 1]);
+    if ((idx & 3) == 0) out[o] = acc;
+#else
+    if ((idx & 3) == 0) BitPairFn<C>{buckets, B, nbits, out}(idx >> 2);
+#endif
+  }
+};
+
 // thread (set, b), b = 0..nbits: term_b = 2^b * S_b (b doublings), the last one 2^nbits * arr[B-1]; the terms are
 // summed by the caller with a short tree.  (A Horner loop over the bits would serialise nbits doublings AND
 // nbits additions in one thread; here the longest chain is nbits doublings.)
@@ -581,6 +724,29 @@ struct BitScaleFn {
     xyzz_t acc = b < nbits ? bitsum[((size_t)set * nbits + b) * stride] : arr[(size_t)set * B + (B - 1)];
     for (uint32_t k = 0; k < b; k++) acc = C::dbl(acc);
     out[idx] = acc;
+  }
+};
+
+// BitScaleFn with one QUAD per term: the chain of b doublings costs 3 multiplication latencies each instead of 9
+template <class C>
+struct BitScaleQuadFn {
+  const xyzz_t* bitsum;
+  size_t stride;
+  const xyzz_t* arr;
+  uint32_t B, nbits;
+  xyzz_t* out;            // [sets][nbits + 1]
+  VDF_HD void operator()(size_t idx) const {
+#if defined(__CUDA_ARCH__)
+    const size_t o = idx >> 2;
+    const uint32_t per = nbits + 1;
+    uint32_t set = (uint32_t)(o / per), b = (uint32_t)(o - (size_t)set * per);
+    xyzz_t acc = b < nbits ? bitsum[((size_t)set * nbits + b) * stride] : arr[(size_t)set * B + (B - 1)];
+#pragma unroll 1
+    for (uint32_t k = 0; k < b; k++) acc = Quad<typename C::field>::dbl(acc);
+    if ((idx & 3) == 0) out[o] = acc;
+#else
+    if ((idx & 3) == 0) BitScaleFn<C>{bitsum, stride, arr, B, nbits, out}(idx >> 2);
+#endif
   }
 };
 
@@ -689,6 +855,45 @@ struct SumWarpFn {
   }
 };
 
+// SumWarpFn with quads (quad.cuh): one WARP per 16 consecutive elements of a row; quad k adds elements 2k and 2k+1, then
+// three shuffle steps add the quads -- 4 quad additions (4 multiplication latencies each) for 16x fewer elements, where
+// the lane-per-element tree spends 5 lane additions (14 latencies each) for 32x.  Index = row * Tw * 32 + warp * 32 +
+// lane with Tw = ceil(cnt / 16); launched with whole warps.
+template <class C>
+struct SumQuadFn {
+  const xyzz_t* in;
+  size_t in_stride;
+  uint32_t cnt, Tw;
+  xyzz_t* out;
+  size_t out_stride;
+  VDF_HD void operator()(size_t idx) const {
+    const size_t w = idx >> 5;
+    const uint32_t row = (uint32_t)(w / Tw), t = (uint32_t)(w - (size_t)row * Tw);
+    const xyzz_t* src = in + (size_t)row * in_stride;
+#if defined(__CUDA_ARCH__)
+    typedef Quad<typename C::field> Q;
+    const unsigned lane = threadIdx.x & 31u, qd = lane >> 2;
+    const uint32_t j = t * 16u + 2u * qd;
+    xyzz_t v = C::identity(), o = C::identity();
+    if (j < cnt) v = src[j];
+    if (j + 1 < cnt) o = src[j + 1];
+    Q::add(v, o);
+#pragma unroll 1
+    for (int d = 4; d >= 1; d >>= 1) {
+      o = Q::down(v, 4 * d);
+      if (qd < (unsigned)d) Q::add(v, o);
+    }
+    if (lane == 0) out[(size_t)row * out_stride + t] = v;
+#else
+    if (idx & 31) return;
+    xyzz_t acc = C::identity();
+    const uint32_t lo = t * 16u, hi = lo + 16u < cnt ? lo + 16u : cnt;
+    for (uint32_t j = lo; j < hi; j++) C::add(acc, src[j]);
+    out[(size_t)row * out_stride + t] = acc;
+#endif
+  }
+};
+
 // rows x cnt  ->  rows x 1 by tree levels, ping-ponging between the two buffers (each at least rows * ceil(cnt / 4)
 // elements after the first level); returns where the result lives and its row stride
 template <class L, class C>
@@ -697,11 +902,20 @@ const xyzz_t* msm_tree_levels(L& L_, uint32_t rows, const xyzz_t* cur, size_t& c
   xyzz_t* dst = (cur == buf_a) ? buf_b : buf_a;
   while (cnt > 1) {
     // small levels are pure latency: the warp tree; big ones are throughput: radix 4 per thread
+#ifdef VDF_NO_QUAD
     const bool warp = cnt > 4 && (size_t)rows * cnt <= 32768;
+#else
+    const bool warp = (size_t)rows * cnt <= 32768;
+#endif
     uint32_t T;
     if (warp) {
+#ifdef VDF_NO_QUAD
       T = (cnt + 31) / 32;
       L_.template run<128>((size_t)rows * T * 32, SumWarpFn<C>{cur, cur_stride, cnt, T, dst, T});
+#else
+      T = (cnt + 15) / 16;
+      L_.template run<128>((size_t)rows * T * 32, SumQuadFn<C>{cur, cur_stride, cnt, T, dst, T});
+#endif
     } else {
       T = (cnt + 3) / 4;
       L_.template run<128>((size_t)rows * T, SumFn<C>{cur, cur_stride, cnt, T, 4u, dst, T});
@@ -739,10 +953,27 @@ template <class L, class C>
 void msm_bit_combine(L& L_, uint32_t NBT, const xyzz_t* bitsum, size_t stride, const xyzz_t* arr, uint32_t B,
                      uint32_t nbits, xyzz_t* out) {
   const uint32_t per = nbits + 1;
+#ifdef VDF_NO_QUAD
   if (per <= 32) {   // one launch: scale and sum in a warp per set
     L_.template run<32>((size_t)NBT * 32, BitScaleSumFn<C>{bitsum, stride, arr, B, nbits, out});
     return;
   }
+#else
+  if (per <= 256) {   // a quad per term for the doublings, then quad tree sums of the terms
+    xyzz_t* terms = L_.template alloc<xyzz_t>((size_t)NBT * per);
+    const uint32_t T1 = (per + 15) / 16;
+    xyzz_t* t1 = L_.template alloc<xyzz_t>((size_t)NBT * T1);
+    L_.template run<32>((size_t)NBT * per * 4, BitScaleQuadFn<C>{bitsum, stride, arr, B, nbits, terms});
+    if (T1 == 1) {
+      L_.template run<32>((size_t)NBT * 32, SumQuadFn<C>{terms, per, per, 1u, out, 1});
+    } else {
+      L_.template run<32>((size_t)NBT * T1 * 32, SumQuadFn<C>{terms, per, per, T1, t1, T1});
+      L_.template run<32>((size_t)NBT * 32, SumQuadFn<C>{t1, T1, T1, 1u, out, 1});
+    }
+    L_.free(terms); L_.free(t1);
+    return;
+  }
+#endif
   xyzz_t* terms = L_.template alloc<xyzz_t>((size_t)NBT * per);
   xyzz_t* t1 = L_.template alloc<xyzz_t>((size_t)NBT * ((per + 3) / 4));
   L_.template run<32>((size_t)NBT * per, BitScaleFn<C>{bitsum, stride, arr, B, nbits, terms});
@@ -779,7 +1010,12 @@ void msm_bit_weighted_sum(L& L_, uint32_t NBT, const xyzz_t* arr, uint32_t B, xy
   uint32_t cnt = B / 4;
   xyzz_t* bs_a = L_.template alloc<xyzz_t>((size_t)rows * cnt);
   xyzz_t* bs_b = L_.template alloc<xyzz_t>((size_t)rows * ((cnt + 3) / 4));
+#ifdef VDF_NO_QUAD
   L_.template run<128>((size_t)rows * cnt, BitPairFn<C>{arr, B, nbits, bs_a});
+#else
+  if ((size_t)rows * cnt <= 65536) L_.template run<128>((size_t)rows * cnt * 4, BitPairQuadFn<C>{arr, B, nbits, bs_a});
+  else L_.template run<128>((size_t)rows * cnt, BitPairFn<C>{arr, B, nbits, bs_a});
+#endif
   size_t cur_stride = cnt;
   const xyzz_t* cur = msm_tree_levels<L, C>(L_, rows, bs_a, cur_stride, cnt, bs_a, bs_b);
   msm_bit_combine<L, C>(L_, NBT, cur, cur_stride, arr, B, nbits, per_set);
@@ -934,6 +1170,7 @@ void msm_accumulate(L& L_, const MsmPlan& p, const affine_t* pts, const ScalarSe
     // The warp level spends 5 lane-additions per record where the serial one spends 1: with many records in long
     // runs (several pieces per bucket) the first levels are throughput-bound, so they stay serial (G = 8).
     const bool long_runs = n_rec > 2 * (size_t)NBK;
+#ifdef VDF_NO_QUAD
     while (n_rec > 64) {
       const bool serial = long_runs && n_rec > 65536;
       const size_t per = serial ? 8 : 32;
@@ -948,6 +1185,23 @@ void msm_accumulate(L& L_, const MsmPlan& p, const affine_t* pts, const ScalarSe
       xyzz_t* tp = pt_a; pt_a = pt_b; pt_b = tp;
       n_rec = 2 * groups;
     }
+#else
+    // serial levels (one lane per 8 records: work-efficient) while the list is long, then RecRunsFn down to one node
+    while (n_rec > 2) {
+      const bool serial = long_runs && n_rec > ((size_t)1 << 17);
+      const size_t per = serial ? 8 : (size_t)RecRunsFn<C>::NS;
+      size_t groups = (n_rec + per - 1) / per;
+      if (!hdr_b) {
+        hdr_b = L_.template alloc<RecHdr>(2 * groups);
+        pt_b = L_.template alloc<xyzz_t>(2 * groups);
+      }
+      if (serial) L_.template run<128>(groups, RecLevelFn<C>{hdr_a, pt_a, n_rec, buckets, hdr_b, pt_b, 8u});
+      else L_.template run<256, 2>(groups * 256, RecRunsFn<C>{hdr_a, pt_a, n_rec, buckets, hdr_b, pt_b});
+      RecHdr* th = hdr_a; hdr_a = hdr_b; hdr_b = th;
+      xyzz_t* tp = pt_a; pt_a = pt_b; pt_b = tp;
+      n_rec = 2 * groups;
+    }
+#endif
   } else {
   const bool small = n_rec <= (1u << 17);
   const uint32_t G = small ? 8u : (p.G < 4 ? 4u : p.G);
@@ -1004,7 +1258,12 @@ void msm_finish(L& L_, const MsmPlan& p, const xyzz_t* buckets, jac_t* out) {
     xyzz_t* A_arr = ra + (size_t)bit_rows * q4;           // [NBT][T0] == [NBT*4][T0/4]
     L_.zero(S_arr, (size_t)NBT * T0 * sizeof(xyzz_t));   // element T0-1 (weight T0) stays the identity
     L_.template run<128>((size_t)NBT * T0, ReduceLevelFn<C>{buckets, p.B, p.B, T0, p.logm, S_arr, A_arr, T0, 0, 0u});
+#ifdef VDF_NO_QUAD
     L_.template run<128>((size_t)bit_rows * q4, BitPairFn<C>{S_arr, T0, nbits, ra});
+#else
+    if ((size_t)bit_rows * q4 <= 65536) L_.template run<128>((size_t)bit_rows * q4 * 4, BitPairQuadFn<C>{S_arr, T0, nbits, ra});
+    else L_.template run<128>((size_t)bit_rows * q4, BitPairFn<C>{S_arr, T0, nbits, ra});
+#endif
     size_t cur_stride = q4;
     const xyzz_t* cur = msm_tree_levels<L, C>(L_, rows, ra, cur_stride, q4, ra, rb);
     xyzz_t* wsum = L_.template alloc<xyzz_t>(NBT);
