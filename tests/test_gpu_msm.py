@@ -280,3 +280,33 @@ def test_msm_submit_wait(gpu_lib):
         _lib.check(gpu_lib.vdfgpu_msm_wait(0))      # nothing in flight
     with pytest.raises(VdfGpuError):
         _lib.check(gpu_lib.vdfgpu_msm_submit(g._h, hosts[0].data_ptr(), n, outs[0].data_ptr(), 9))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cid", CURVES)
+@pytest.mark.parametrize("table", [False, True])
+def test_msm_equal_points_special_cases_of_the_group_law(gpu_lib, cid, table):
+    """Every generator the same point P: every bucket sum is a multiple of P, so the tree sums of the bucket reduction
+    (quad additions, csrc/quad.cuh) keep meeting P + P (the doubling branch), and with P, -P alternating under equal
+    scalars every bucket cancels to the identity (the identity branches).  Expected: (sum of the scalars) * P."""
+    cv = O.CURVES[cid]
+    n = 4096
+    P = cv.mul(77, cv.gen)
+    # distinct small scalars: bucket j of window 0 receives exactly one copy of P
+    sc = [i + 1 for i in range(n)]
+    g = G.Generators.from_points(cid, [P] * n, table=table)
+    assert g.commit(sc) == cv.mul(sum(sc) % cv.order, P)
+    # the same scalar everywhere: one bucket per window holds n * P, all others are empty
+    s = (1 << 200) + 12345
+    assert g.commit([s] * n) == cv.mul(s * n % cv.order, P)
+    g.close()
+    # P, -P, P, -P ... with pairwise equal scalars: everything cancels
+    rng = O.XorShiftRng()
+    half = rand_scalars(rng, cv.order, n // 2)
+    sc2 = [half[i // 2] for i in range(n)]
+    g = G.Generators.from_points(cid, [P if i % 2 == 0 else cv.neg(P) for i in range(n)], table=table)
+    assert g.commit(sc2) is None
+    # ... and with one survivor
+    sc2[-1] = (sc2[-1] + 5) % cv.order
+    assert g.commit(sc2) == cv.mul(cv.order - 5, P)
+    g.close()

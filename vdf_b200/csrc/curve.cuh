@@ -108,8 +108,8 @@ struct Curve {
 #endif
 
 #ifndef VDF_MADD_MUL
-#define VDF_MADD_MUL mul_call
-#define VDF_MADD_SQR sqr_call
+#define VDF_MADD_MUL mul_val   // by value: operands and result stay in registers across the call (mul_call: via the stack)
+#define VDF_MADD_SQR sqr_val
 #endif
   // madd with the multiplier called out of line (same arithmetic; used by the accumulate kernel)
   static VDF_HD void madd_call(xyzz_t& acc, const fe& x2, const fe& y2) {

@@ -905,7 +905,10 @@ const xyzz_t* msm_tree_levels(L& L_, uint32_t rows, const xyzz_t* cur, size_t& c
 #ifdef VDF_NO_QUAD
     const bool warp = cnt > 4 && (size_t)rows * cnt <= 32768;
 #else
-    const bool warp = (size_t)rows * cnt <= 32768;
+#ifndef VDF_SUMQUAD_MAX
+#define VDF_SUMQUAD_MAX 32768
+#endif
+    const bool warp = (size_t)rows * cnt <= VDF_SUMQUAD_MAX;
 #endif
     uint32_t T;
     if (warp) {
@@ -1188,7 +1191,10 @@ void msm_accumulate(L& L_, const MsmPlan& p, const affine_t* pts, const ScalarSe
 #else
     // serial levels (one lane per 8 records: work-efficient) while the list is long, then RecRunsFn down to one node
     while (n_rec > 2) {
-      const bool serial = long_runs && n_rec > ((size_t)1 << 17);
+#ifndef VDF_REC_SERIAL_ABOVE
+#define VDF_REC_SERIAL_ABOVE (1u << 19)   // measured: Nova fold step 0.604 (2^17) -> 0.573 ms (2^19), profiles/r2_experiments.md
+#endif
+      const bool serial = long_runs && n_rec > (size_t)VDF_REC_SERIAL_ABOVE;
       const size_t per = serial ? 8 : (size_t)RecRunsFn<C>::NS;
       size_t groups = (n_rec + per - 1) / per;
       if (!hdr_b) {
