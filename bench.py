@@ -264,6 +264,10 @@ def r1cs_hbm_measurements(lib, _lib, torch, log2rows: int = 21):
     b_ct = 36 * nnz + 4 * (3 * cons + 1) + 2 * 32 * (vars_ + 1 + io) + 32 * cons
     b_mv = 36 * nnz + 4 * (3 * cons + 1) + 32 * (vars_ + 1 + io) + 3 * 32 * cons
     b_fd = 96 * (vars_ + cons)
+    # scaled row table (read cons, write 3 cons) + per entry: its stacked row (u32), the value, one gathered table element
+    b_br = 32 * 4 * cons + (4 + 32 + 32) * nnz + 4 * (vars_ + 1 + io + 1) + 32 * (vars_ + 1 + io)
+    rr3 = rand_fe_dev(torch, 3)
+    Mt = torch.zeros((vars_ + 1 + io, 4), dtype=torch.int64, device="cuda")
     for mix, bval in (("random_B", rnd), ("unit", one)):
         b_vals = np.frombuffer(bval * cons, dtype=np.uint8)
         h = ctypes.c_void_p()
@@ -274,8 +278,10 @@ def r1cs_hbm_measurements(lib, _lib, torch, log2rows: int = 21):
                                           ctypes.byref(h)))
         t_ct = cuda_timed(torch, lambda: _lib.check(lib.vdfgpu_cross_term_dev(h, W1.data_ptr(), uX1.data_ptr(), W2.data_ptr(), uX2.data_ptr(), T.data_ptr())))
         t_mv = cuda_timed(torch, lambda: _lib.check(lib.vdfgpu_multiply_vec_dev(h, W1.data_ptr(), uX1.data_ptr(), ABC.data_ptr())))
+        # Spartan's inner sum-check table: transposed product over the column view
+        t_br = cuda_timed(torch, lambda: _lib.check(lib.vdfgpu_r1cs_bind_rows_dev(h, E1.data_ptr(), rr3.data_ptr(), ABC.data_ptr(), Mt.data_ptr())))
         out = {"coefficients": "A = +1, B = full-size random, C = +1 / -1" if mix == "random_B" else "all +1 / -1 (step-circuit mix)"}
-        for name, t, b in (("cross_term", t_ct, b_ct), ("multiply_vec", t_mv, b_mv)):
+        for name, t, b in (("cross_term", t_ct, b_ct), ("multiply_vec", t_mv, b_mv), ("bind_rows", t_br, b_br)):
             out[name] = {"ms": t * 1e3, "algorithmic_bytes": b, "achieved_gbs": b / t / 1e9, "frac_of_hbm": b / t / 1e9 / peak}
         res[mix] = out
         _lib.check(lib.vdfgpu_r1cs_destroy(h))

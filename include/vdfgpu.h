@@ -161,6 +161,16 @@ int vdfgpu_fold(int field, void* W1_host, const void* W2_host, size_t nW, void* 
 /* device-pointer variants (no copies, no synchronisation): what a device-resident prover and bench.py's
  * HBM-roofline leg call.  uX = [u | X] (1 + io elements), uX2 = [1 | X2]. */
 int vdfgpu_multiply_vec_dev(const vdfgpu_r1cs* s, const void* W_dev, const void* uX_dev, void* AzBzCz_dev);
+
+/* Spartan's inner sum-check table (nova-snark 0.8 spartan_with_ipa_pc: compute_eval_table_sparse
+ * combined with r_A, r_B, r_C [R], reached from CompressedSNARK::prove, /root/reference/src/nova/proof.rs:363):
+ *   out[y] = sum_x eq_rows[x] * (r_abc[0] A[x,y] + r_abc[1] B[x,y] + r_abc[2] C[x,y]),  y < vars + 1 + io.
+ * eq_rows: cons elements (the eq table of the outer challenge, vdfgpu_eq_evals), r_abc: 3 elements, out: vars+1+io
+ * elements, all 32-byte Montgomery.  The _dev form works on device pointers on the calling thread's stream and needs
+ * a scratch vector of 3 * cons elements. */
+int vdfgpu_r1cs_bind_rows(const vdfgpu_r1cs* s, const void* eq_rows_host, const void* r_abc_host, void* out_host);
+int vdfgpu_r1cs_bind_rows_dev(const vdfgpu_r1cs* s, const void* eq_rows_dev, const void* r_abc_dev, void* scratch_dev,
+                              void* out_dev);
 int vdfgpu_cross_term_dev(const vdfgpu_r1cs* s, const void* W1_dev, const void* uX1_dev, const void* W2_dev,
                           const void* uX2_dev, void* T_dev);
 int vdfgpu_fold_dev(int field, void* W1_dev, const void* W2_dev, size_t nW, void* E1_dev, const void* T_dev,

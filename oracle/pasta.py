@@ -460,6 +460,17 @@ class R1CSShape:
             out.append(v)
         return out
 
+    def bind_rows(self, eq_rows: Sequence[int], r_abc: Sequence[int]) -> List[int]:
+        """out[y] = sum_x eq_rows[x] (rA A[x,y] + rB B[x,y] + rC C[x,y]): the table of Spartan's inner sum-check
+        (nova-snark 0.8 spartan_with_ipa_pc, compute_eval_table_sparse combined with r_A, r_B, r_C [R]; reached from
+        CompressedSNARK::prove, src/nova/proof.rs:363).  A unique mathematical object: restated from the definition."""
+        assert len(eq_rows) == self.num_cons and len(r_abc) == 3
+        out = [0] * (self.num_vars + 1 + self.num_io)
+        for M, rm in zip((self.A, self.B, self.C), r_abc):
+            for (r, c, val) in M:
+                out[c] = (out[c] + rm * val % self.m * eq_rows[r]) % self.m
+        return out
+
     def z_of(self, W, u, X):
         return list(W) + [u] + list(X)
 

@@ -108,6 +108,10 @@ extern "C" {
                        t_host: *const c_void, n_e: size_t, r32_host: *const c_void) -> c_int;
     pub fn vdfgpu_multiply_vec_dev(s: *const vdfgpu_r1cs, w_dev: *const c_void, ux_dev: *const c_void,
                                    az_bz_cz_dev: *mut c_void) -> c_int;
+    pub fn vdfgpu_r1cs_bind_rows(s: *const vdfgpu_r1cs, eq_rows_host: *const c_void, r_abc_host: *const c_void,
+                                 out_host: *mut c_void) -> c_int;
+    pub fn vdfgpu_r1cs_bind_rows_dev(s: *const vdfgpu_r1cs, eq_rows_dev: *const c_void, r_abc_dev: *const c_void,
+                                     scratch_dev: *mut c_void, out_dev: *mut c_void) -> c_int;
     pub fn vdfgpu_cross_term_dev(s: *const vdfgpu_r1cs, w1_dev: *const c_void, ux1_dev: *const c_void,
                                  w2_dev: *const c_void, ux2_dev: *const c_void, t_dev: *mut c_void) -> c_int;
     pub fn vdfgpu_fold_dev(field: c_int, w1_dev: *mut c_void, w2_dev: *const c_void, n_w: size_t, e1_dev: *mut c_void,

@@ -95,3 +95,107 @@ def test_ipa_round_building_blocks(gpu_lib, cid):
     assert SP.points_lincomb(cid, O.affines_to_bytes(cv, L[:4]), O.affines_to_bytes(cv, R[:4]), 0, 1) == O.affines_to_bytes(cv, R[:4])
     assert SP.points_lincomb(cid, O.affines_to_bytes(cv, L[:4]), O.affines_to_bytes(cv, R[:4]), 1, 0) == O.affines_to_bytes(cv, L[:4])
 
+
+
+def _gpu_shape(shape):
+    from vdf_b200 import nova as N
+    fid = O.FIELD_FP if shape.m == O.P else O.FIELD_FQ
+    return N.R1CSShape(fid, shape.num_cons, shape.num_vars, shape.num_io, shape.A, shape.B, shape.C)
+
+
+@pytest.mark.parametrize("fid", [O.FIELD_FP, O.FIELD_FQ])
+def test_bind_rows_matches_oracle(gpu_lib, fid):
+    """The inner sum-check's table: transposed sparse product over the column view of the CSR; the step circuit's
+    constant column holds an entry per round (the heavy column a warp sums cooperatively)."""
+    m = O.MODULUS[fid]
+    py = random.Random(60 + fid)
+    for t, aug in ((1, 0), (100, 0), (10, 300)):   # t = 100: the constant column has > 64 entries (BindHeavyFn)
+        shape, W, X, _ = O.make_step_instance(fid, t, O.State(py.randrange(m), py.randrange(m), t), aug_cons=aug)
+        gs = _gpu_shape(shape)
+        eq = [py.randrange(m) for _ in range(shape.num_cons)]
+        for r_abc in ([py.randrange(m) for _ in range(3)], [1, 0, 0], [0, 0, m - 1]):
+            assert gs.bind_rows(eq, r_abc) == shape.bind_rows(eq, r_abc)
+        with pytest.raises(ValueError):
+            gs.bind_rows(eq[:-1], [1, 2, 3])
+        gs.close()
+
+
+def _interp(points, r, m):
+    """value at r of the polynomial through (x_k, y_k)"""
+    acc = 0
+    for k, (xk, yk) in enumerate(points):
+        num, den = 1, 1
+        for j, (xj, _) in enumerate(points):
+            if j != k:
+                num = num * (r - xj) % m
+                den = den * (xk - xj) % m
+        acc = (acc + yk * num * pow(den, -1, m)) % m
+    return acc
+
+
+def _verify_rounds(claim, evals, rs, m, cubic):
+    """The sum-check verifier: e(0) + e(1) = claim, next claim = e(r); e(1) is implied by the claim."""
+    for e, r in zip(evals, rs):
+        e1 = (claim - e[0]) % m
+        pts = [(0, e[0]), (1, e1), (2, e[1])] + ([(3, e[2])] if cubic else [])
+        claim = _interp(pts, r, m)
+    return claim
+
+
+def test_spartan_sumcheck_phases_on_a_folded_relaxed_instance(gpu_lib):
+    """Both sum-check phases of RelaxedR1CSSNARK::prove (nova-snark spartan_with_ipa_pc [R], from
+    CompressedSNARK::prove, src/nova/proof.rs:363) on the GPU building blocks, checked by a verifier written here:
+    outer  sum_x eq(tau, x) (Az(x) Bz(x) - (u Cz(x) + E(x))) = 0,
+    inner  sum_y (rA A + rB B + rC C)(rx, y) z(y) = rA Az(rx) + rB Bz(rx) + rC Cz(rx),
+    on an instance with u != 1 and E != 0 (two step instances folded by the oracle)."""
+    from vdf_b200 import nova as N
+    fid, m = O.FIELD_FQ, O.Q
+    py = random.Random(77)
+    shape, W1, X1, _ = O.make_step_instance(fid, 12, O.State(5, 6, 12), aug_cons=100)
+    _, W2, X2, _ = O.make_step_instance(fid, 12, O.State(9, 1, 12), aug_cons=100)
+    r_fold = py.randrange(1 << 128)
+    T = shape.cross_term(W1, 1, X1, W2, X2)
+    W, E = O.fold_vec(W1, W2, r_fold, m), [r_fold * t % m for t in T]
+    X, u = O.fold_vec(X1, X2, r_fold, m), (1 + r_fold) % m
+    assert shape.is_sat_relaxed(W, E, u, X) and any(E)
+    z = shape.z_of(W, u, X)
+    gs = _gpu_shape(shape)
+    Az, Bz, Cz = gs.multiply_vec(z)
+
+    def pad(v, ell):
+        return list(v) + [0] * ((1 << ell) - len(v))
+
+    def challenge(rnd, evals):
+        return (sum(evals) * 0x9E3779B97F4A7C15 + rnd + 999) % m
+
+    # outer phase
+    ell_x = max(1, (shape.num_cons - 1).bit_length())
+    tau = [py.randrange(m) for _ in range(ell_x)]
+    D = [(u * c + e) % m for c, e in zip(Cz, E)]
+    tabs = [SP.eq_evals(fid, tau), pad(Az, ell_x), pad(Bz, ell_x), pad(D, ell_x)]
+    evals, rx, fin = SP.sumcheck(fid, tabs, challenge)
+    last = _verify_rounds(0, evals, rx, m, cubic=True)
+    assert last == fin[0] * (fin[1] * fin[2] - fin[3]) % m
+    assert fin[0] == O.poly_evaluate(O.eq_evals(tau, m), rx, m)
+    claim_Az, claim_Bz = fin[1], fin[2]
+    claim_Cz = SP.poly_evaluate(fid, pad(Cz, ell_x), rx)
+    assert fin[3] == (u * claim_Cz + SP.poly_evaluate(fid, pad(E, ell_x), rx)) % m
+
+    # inner phase
+    r_abc = [py.randrange(m) for _ in range(3)]
+    eq_rx = SP.eq_evals(fid, rx)[:shape.num_cons]
+    Mt = gs.bind_rows(eq_rx, r_abc)
+    ell_y = max(1, (len(z) - 1).bit_length())
+    claim = (r_abc[0] * claim_Az + r_abc[1] * claim_Bz + r_abc[2] * claim_Cz) % m
+    evals, ry, fin = SP.sumcheck(fid, [pad(Mt, ell_y), pad(z, ell_y)], challenge)
+    last = _verify_rounds(claim, evals, ry, m, cubic=False)
+    assert last == fin[0] * fin[1] % m
+    # what the verifier recomputes itself: the sparse matrices at (rx, ry), and z(ry)
+    eq_ry = O.eq_evals(ry, m)
+    eq_rx_full = O.eq_evals(rx, m)
+    want = 0
+    for M, rm in zip((shape.A, shape.B, shape.C), r_abc):
+        want = (want + rm * sum(v * eq_rx_full[r] % m * eq_ry[c] for r, c, v in M)) % m
+    assert fin[0] == want
+    assert fin[1] == O.poly_evaluate(pad(z, ell_y), ry, m)
+    gs.close()

@@ -219,3 +219,18 @@ def test_sumcheck_oracle_is_a_sound_sumcheck():
     assert sum(eq) % m == 1
     assert eq[0b1010] == r[0] * (1 - r[1]) * r[2] * (1 - r[3]) % m
     assert O.eq_evals([], m) == [1]
+
+
+def test_bind_rows_is_the_transposed_product():
+    """sum_y bind_rows(eq, r)[y] z[y] = sum_m r_m <eq, M z>: the identity Spartan's inner sum-check rests on."""
+    import random
+    py = random.Random(3)
+    for fid in (O.FIELD_FP, O.FIELD_FQ):
+        m = O.MODULUS[fid]
+        shape, W, X, _ = O.make_step_instance(fid, 7, O.State(1, 2, 7), aug_cons=40)
+        z = shape.z_of(W, 1, X)
+        eq = [py.randrange(m) for _ in range(shape.num_cons)]
+        r = [py.randrange(m) for _ in range(3)]
+        lhs = sum(a * b for a, b in zip(shape.bind_rows(eq, r), z)) % m
+        rhs = sum(rm * sum(e * v for e, v in zip(eq, Mz)) for rm, Mz in zip(r, shape.multiply_vec(z))) % m
+        assert lhs == rhs

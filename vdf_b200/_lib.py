@@ -63,6 +63,8 @@ PROTOTYPES = {
     "vdfgpu_commit_T": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vdfgpu_fold": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vdfgpu_multiply_vec_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vdfgpu_r1cs_bind_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vdfgpu_r1cs_bind_rows_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vdfgpu_cross_term_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vdfgpu_fold_dev": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vdfgpu_running_create": (c_int, [c_void_p, c_void_p, POINTER(c_void_p)]),

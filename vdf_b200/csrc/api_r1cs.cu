@@ -15,8 +15,14 @@ struct vdfgpu_r1cs {
   uint32_t* row_ptr = nullptr;  // [3*cons+1]
   uint32_t* col = nullptr;
   vdf::fe* val = nullptr;
+  uint32_t* col_ptr = nullptr;    // column view (csr_to_csc): [vars + 1 + io + 1]
+  uint32_t* csc_row = nullptr;    // [nnz]
+  vdf::fe* csc_val = nullptr;     // [nnz]
+  uint32_t* heavy = nullptr;      // [n_heavy]
+  uint32_t n_heavy = 0;
   mutable int refs = 0;   // running instances holding this shape (vdfgpu_r1cs_destroy refuses while > 0)
   vdf::CsrView view() const { return vdf::CsrView{row_ptr, col, val, cons, vars, io}; }
+  vdf::CscView col_view() const { return vdf::CscView{col_ptr, csc_row, csc_val, heavy, vdf::HostCsc::HEAVY}; }
 };
 
 struct vdfgpu_running {
@@ -130,9 +136,20 @@ int vdfgpu_r1cs_create(int field, size_t num_cons, size_t num_vars, size_t num_i
       h2d(s->row_ptr, row_ptr.data(), (R + 1) * 4, cur_stream());
       h2d(s->col, col.data(), nnz * 4, cur_stream());
       h2d(s->val, val.data(), nnz * 32, cur_stream());
+      const HostCsc csc = csr_to_csc(csr, ncols);
+      s->n_heavy = (uint32_t)csc.heavy.size();
+      VDF_CUDA_CHECK(cudaMalloc((void**)&s->col_ptr, (ncols + 1) * 4));
+      VDF_CUDA_CHECK(cudaMalloc((void**)&s->csc_row, (nnz ? nnz : 1) * 4));
+      VDF_CUDA_CHECK(cudaMalloc((void**)&s->csc_val, (nnz ? nnz : 1) * 32));
+      VDF_CUDA_CHECK(cudaMalloc((void**)&s->heavy, (s->n_heavy ? s->n_heavy : 1) * 4));
+      h2d(s->col_ptr, csc.col_ptr.data(), (ncols + 1) * 4, cur_stream());
+      h2d(s->csc_row, csc.srow.data(), nnz * 4, cur_stream());
+      h2d(s->csc_val, csc.val.data(), nnz * 32, cur_stream());
+      h2d(s->heavy, csc.heavy.data(), (size_t)s->n_heavy * 4, cur_stream());
       sync_after_unlock(cur_stream());
     } catch (...) {
       cudaFree(s->row_ptr); cudaFree(s->col); cudaFree(s->val);
+      cudaFree(s->col_ptr); cudaFree(s->csc_row); cudaFree(s->csc_val); cudaFree(s->heavy);
       delete s;
       throw;
     }
@@ -149,6 +166,7 @@ int vdfgpu_r1cs_destroy(vdfgpu_r1cs* s) {
       cudaDeviceSynchronize();
     }
     cudaFree(s->row_ptr); cudaFree(s->col); cudaFree(s->val);
+    cudaFree(s->col_ptr); cudaFree(s->csc_row); cudaFree(s->csc_val); cudaFree(s->heavy);
     delete s;
   });
 }
@@ -243,6 +261,50 @@ int vdfgpu_multiply_vec_dev(const vdfgpu_r1cs* s, const void* W_dev, const void*
     fe* out = reinterpret_cast<fe*>(AzBzCz_dev);
     launch_multiply_vec(L, s, ZView{reinterpret_cast<const fe*>(W_dev), ux, ux + 1}, out, out + s->cons,
                         out + 2 * (size_t)s->cons);
+    c.launches += L.launches;
+  });
+}
+
+static void launch_bind_rows(CudaLaunch& L, const vdfgpu_r1cs* s, const fe* eq, const fe* coef, fe* eq3, fe* out) {
+  const size_t ncols = (size_t)s->vars + 1 + s->io;
+  const CscView v = s->col_view();
+  if (s->field == VDFGPU_FP) {
+    L.run<128>(3 * (size_t)s->cons, ScaleRowsFn<Fp>{eq, coef, s->cons, eq3});
+    L.run<128>(ncols, BindRowsFn<Fp>{v, eq3, out});
+    if (s->n_heavy) L.run<128>((size_t)s->n_heavy * 32, BindHeavyFn<Fp>{v, eq3, out});
+  } else {
+    L.run<128>(3 * (size_t)s->cons, ScaleRowsFn<Fq>{eq, coef, s->cons, eq3});
+    L.run<128>(ncols, BindRowsFn<Fq>{v, eq3, out});
+    if (s->n_heavy) L.run<128>((size_t)s->n_heavy * 32, BindHeavyFn<Fq>{v, eq3, out});
+  }
+}
+
+int vdfgpu_r1cs_bind_rows(const vdfgpu_r1cs* s, const void* eq_rows_host, const void* r_abc_host, void* out_host) {
+  return guarded([&] {
+    if (!s || !eq_rows_host || !r_abc_host || !out_host) throw ArgError("r1cs_bind_rows: null pointer");
+    require_ready();
+    Context& c = ctx();
+    CudaLaunch L(cur_stream());
+    const size_t ncols = (size_t)s->vars + 1 + s->io;
+    DevBuf<fe> eq(s->cons, cur_stream()), coef(3, cur_stream()), eq3(3 * (size_t)s->cons, cur_stream()), out(ncols, cur_stream());
+    h2d(eq.p, eq_rows_host, (size_t)s->cons * 32, cur_stream());
+    h2d(coef.p, r_abc_host, 96, cur_stream());
+    launch_bind_rows(L, s, eq.p, coef.p, eq3.p, out.p);
+    d2h(out_host, out.p, ncols * 32, cur_stream());
+    c.launches += L.launches;
+    sync_after_unlock(cur_stream());
+  });
+}
+
+int vdfgpu_r1cs_bind_rows_dev(const vdfgpu_r1cs* s, const void* eq_rows_dev, const void* r_abc_dev, void* scratch_dev,
+                              void* out_dev) {
+  return guarded([&] {
+    if (!s || !eq_rows_dev || !r_abc_dev || !scratch_dev || !out_dev) throw ArgError("r1cs_bind_rows_dev: null pointer");
+    require_ready();
+    Context& c = ctx();
+    CudaLaunch L(cur_stream());
+    launch_bind_rows(L, s, reinterpret_cast<const fe*>(eq_rows_dev), reinterpret_cast<const fe*>(r_abc_dev),
+                     reinterpret_cast<fe*>(scratch_dev), reinterpret_cast<fe*>(out_dev));
     c.launches += L.launches;
   });
 }

@@ -115,6 +115,79 @@ struct CrossTermFn {
   }
 };
 
+// ---- transposed product for Spartan's inner sum-check ---------------------------------------
+// M(y) = sum_x eq(x) * (rA A[x,y] + rB B[x,y] + rC C[x,y]) for every column y: nova-snark's
+// compute_eval_table_sparse combined with the three challenges [R], reached from CompressedSNARK::prove
+// (src/nova/proof.rs:363).  The scaled row table eq3[mat * cons + x] = r_mat * eq(x) first, then one THREAD per column
+// over the column view (40 bytes per entry read in order + one gathered table element); the few heavy columns (the
+// constant column of the step circuit holds one entry per round) are left to one WARP each: lanes stride over the
+// entries, a shuffle tree adds the lanes.
+struct CscView {
+  const uint32_t* col_ptr;  // [ncols + 1]
+  const uint32_t* srow;     // stacked row = mat * cons + row
+  const fe* val;            // column order
+  const uint32_t* heavy;    // columns with more than heavy_above entries
+  uint32_t heavy_above;
+};
+
+template <class F>
+struct ScaleRowsFn {
+  const fe* eq;     // [cons]
+  const fe* coef;   // [3]
+  uint32_t cons;
+  fe* eq3;          // [3 * cons]
+  VDF_HD void operator()(size_t idx) const {
+    const uint32_t mat = (uint32_t)(idx / cons), row = (uint32_t)(idx - (size_t)mat * cons);
+    fe_store(eq3 + idx, F::mul(fe_load(coef + mat), fe_load(eq + row)));
+  }
+};
+
+template <class F>
+struct BindRowsFn {   // index = column
+  CscView m;
+  const fe* eq3;
+  fe* out;          // [ncols]
+  VDF_HD void operator()(size_t col) const {
+    const uint32_t lo = m.col_ptr[col], hi = m.col_ptr[col + 1];
+    if (hi - lo > m.heavy_above) return;   // BindHeavyFn's
+    const fe one = F::one(), minus_one = F::neg(F::one());
+    fe acc = F::zero();
+    for (uint32_t k = lo; k < hi; k++)
+      acc = mul_acc<F>(acc, fe_load(m.val + k), fe_load_gather(eq3 + m.srow[k]), one, minus_one);
+    fe_store(out + col, acc);
+  }
+};
+
+template <class F>
+struct BindHeavyFn {   // index = (position in the heavy list) * 32 + lane; launched with whole warps
+  CscView m;
+  const fe* eq3;
+  fe* out;
+  VDF_HD void operator()(size_t idx) const {
+    const uint32_t col = m.heavy[idx >> 5];
+    const uint32_t lo = m.col_ptr[col], hi = m.col_ptr[col + 1];
+    const fe one = F::one(), minus_one = F::neg(F::one());
+    fe acc = F::zero();
+#if defined(__CUDA_ARCH__)
+    const unsigned lane = (unsigned)idx & 31u;
+    for (uint32_t k = lo + lane; k < hi; k += 32)
+      acc = mul_acc<F>(acc, fe_load(m.val + k), fe_load_gather(eq3 + m.srow[k]), one, minus_one);
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+      fe o;
+#pragma unroll
+      for (int q = 0; q < 8; q++) o.v[q] = __shfl_down_sync(0xffffffffu, acc.v[q], d);
+      acc = F::add(acc, o);
+    }
+    if (lane == 0) fe_store(out + col, acc);
+#else
+    if (idx & 31) return;
+    for (uint32_t k = lo; k < hi; k++) acc = mul_acc<F>(acc, fe_load(m.val + k), fe_load(eq3 + m.srow[k]), one, minus_one);
+    fe_store(out + col, acc);
+#endif
+  }
+};
+
 // a[i] <- a[i] + r * b[i] over two vectors in one launch (W with W2, E with T)
 template <class F>
 struct FoldFn {

@@ -55,6 +55,16 @@ class R1CSShape:
                                                    *[_lib.as_ptr(o) for o in outs]))
         return tuple(fes_from_bytes(bytes(o), self.m) for o in outs)
 
+    def bind_rows(self, eq_rows: Sequence[int], r_abc: Sequence[int]) -> List[int]:
+        """Spartan's inner sum-check table: out[y] = sum_x eq_rows[x] (rA A[x,y] + rB B[x,y] + rC C[x,y])
+        (nova-snark compute_eval_table_sparse + the three challenges; CompressedSNARK::prove, src/nova/proof.rs:363)."""
+        if len(eq_rows) != self.num_cons or len(r_abc) != 3:
+            raise ValueError("eq_rows needs one entry per constraint and r_abc three challenges")
+        out = bytearray((self.num_vars + 1 + self.num_io) * 32)
+        _lib.check(_lib.load().vdfgpu_r1cs_bind_rows(self._h, _lib.as_ptr(fes_to_bytes(eq_rows, self.m)),
+                                                     _lib.as_ptr(fes_to_bytes(r_abc, self.m)), _lib.as_ptr(out)))
+        return fes_from_bytes(bytes(out), self.m)
+
     def commit_T(self, gens: Optional[Generators], W1: Sequence[int], u1: int, X1: Sequence[int],
                  W2: Sequence[int], X2: Sequence[int]) -> Tuple[List[int], Affine]:
         """Cross-term T and its commitment (u2 = 1 for the fresh instance)."""
