@@ -199,3 +199,48 @@ def test_spartan_sumcheck_phases_on_a_folded_relaxed_instance(gpu_lib):
     assert fin[0] == want
     assert fin[1] == O.poly_evaluate(pad(z, ell_y), ry, m)
     gs.close()
+
+
+@pytest.mark.parametrize("cid", [O.CURVE_PALLAS, O.CURVE_VESTA])
+def test_inner_product_argument_end_to_end(gpu_lib, cid):
+    """All log2(n) rounds of an inner-product argument (the polynomial-evaluation argument of spartan_with_ipa_pc [R],
+    from CompressedSNARK::prove, src/nova/proof.rs:363) on the GPU blocks: per round two cross inner products, two
+    commitments over generator halves (the drop-in MSM symbol), the folds of a, b and of the generators.  The verifier
+    below uses Python integers only: P' = r^2 L + P + r^-2 R per round, and at the end P_final = a (G_final + b U)."""
+    from vdf_b200 import msm as G
+    from vdf_b200.encoding import CURVE_BASE, point_from_bytes
+    cv = O.CURVES[cid]
+    fid = 1 if cid == 0 else 0
+    m = cv.order
+    py = random.Random(90 + cid)
+    n = 64
+    gens = [cv.mul(py.randrange(1, m), cv.gen) for _ in range(n)]
+    U = cv.mul(py.randrange(1, m), cv.gen)
+    a = [py.randrange(m) for _ in range(n)]
+    b = O.eq_evals([py.randrange(m) for _ in range(6)], m)      # the evaluation point's eq table
+    c = SP.inner_product(fid, a, b)
+
+    def commit(points_bytes, scalars):
+        raw = G.mult_pippenger(cid, points_bytes, O.fes_to_bytes(scalars, m), True)
+        return point_from_bytes(raw, CURVE_BASE[cid])
+
+    Gb = O.affines_to_bytes(cv, gens)
+    P = cv.add(commit(Gb, a), cv.mul(c, U))                     # what the verifier holds: commitment + claimed value
+    assert commit(Gb, a) == cv.msm(a, gens)
+    while n > 1:
+        h = n // 2
+        a_lo, a_hi, b_lo, b_hi = a[:h], a[h:], b[:h], b[h:]
+        G_lo, G_hi = Gb[:72 * h], Gb[72 * h:]
+        cL, cR = SP.inner_product(fid, a_lo, b_hi), SP.inner_product(fid, a_hi, b_lo)
+        L = cv.add(commit(G_hi, a_lo), cv.mul(cL, U))
+        R = cv.add(commit(G_lo, a_hi), cv.mul(cR, U))
+        r = py.randrange(1, m)                                   # the transcript's challenge
+        r_inv = pow(r, -1, m)
+        a = SP.vec_lincomb(fid, a_lo, a_hi, r, r_inv)
+        b = SP.vec_lincomb(fid, b_lo, b_hi, r_inv, r)
+        Gb = SP.points_lincomb(cid, G_lo, G_hi, r_inv, r)
+        # verifier
+        P = cv.add(cv.add(cv.mul(r * r % m, L), P), cv.mul(r_inv * r_inv % m, R))
+        n = h
+    G_final = O.affine_from_bytes(cv, Gb[:72])
+    assert P == cv.mul(a[0], cv.add(G_final, cv.mul(b[0], U)))
