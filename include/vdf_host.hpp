@@ -164,6 +164,14 @@ class R1CSShape {
     ok_or_throw(vdfgpu_multiply_vec(h_, z.data(), p.Az.data(), p.Bz.data(), p.Cz.data()), "vdfgpu_multiply_vec");
     return p;
   }
+  // spartan_with_ipa_pc's compute_eval_table_sparse combined with (r_A, r_B, r_C): the inner sum-check's table,
+  // out[y] = sum_x eq_rows[x] (r_A A[x,y] + r_B B[x,y] + r_C C[x,y]) over the columns of z
+  std::vector<Fe> bind_rows(const std::vector<Fe>& eq_rows, const std::array<Fe, 3>& r_abc) const {
+    if (eq_rows.size() != cons_) throw std::invalid_argument("bind_rows: one eq entry per constraint");
+    std::vector<Fe> out(vars_ + 1 + io_);
+    ok_or_throw(vdfgpu_r1cs_bind_rows(h_, eq_rows.data(), r_abc.data(), out.data()), "vdfgpu_r1cs_bind_rows");
+    return out;
+  }
   // commit_T(gens, U1, W1, U2, W2) -> (T, comm_T); u2 = 1
   std::pair<std::vector<Fe>, Point> commit_T(const Generators& gens, const std::vector<Fe>& W1, const Fe& u1,
                                              const std::vector<Fe>& X1, const std::vector<Fe>& W2,
