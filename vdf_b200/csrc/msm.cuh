@@ -84,7 +84,14 @@ static inline uint32_t msm_pick_c(size_t n, bool table) {
   uint32_t lg = 0;
   while (((size_t)1 << (lg + 1)) <= n) lg++;
   int c;
-  if (table) c = (int)lg - 1;   // one shared bucket set of 2^(c-1) ~ n/4 buckets: reduction stays ~10 %
+  if (table) {
+    c = (int)lg - 1;            // one shared bucket set of 2^(c-1) ~ n/4 buckets: reduction stays ~10 %
+    // 2^15 .. 2^18 points: one bit less.  The bucket reduction is a latency chain that grows with the bucket count
+    // while the accumulation is still small; c = 16 and c = 17 even have the same 16 windows.  Measured with
+    // tools/sweep_window_bits.py (uniform scalars, us per commitment): 2^15: 410 -> 381 (c = 13), 2^17: 774 -> 758
+    // (c = 15), 2^18: 1280 -> 1187 (c = 16); 2^16 lands on c = 15 either way (14 is skipped below).
+    if (lg >= 15 && lg <= 18) c = (int)lg - 2;
+  }
   else c = (int)lg - 6;         // W bucket sets of 2^(c-1) buckets each
   if (c < 4) c = 4;
   if (c > 20) c = 20;
