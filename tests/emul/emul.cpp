@@ -266,7 +266,8 @@ int emul_minroot_witness(int field, const void* results, uint64_t t, size_t n, v
   return 0;
 }
 
-// R1CS: mode 0 = multiply_vec (out = Az|Bz|Cz, 3*cons elements, z1 only), mode 1 = cross-term T (cons elements)
+// R1CS: mode 0 = multiply_vec (out = Az|Bz|Cz, 3*cons elements, z1 only), mode 1 = cross-term T (cons elements),
+// mode 2 = bind_rows (W1 = eq table of cons elements, u1 = the three challenges; out = vars+1+io elements)
 int emul_r1cs(int field, int mode, size_t num_cons, size_t num_vars, size_t num_io, const uint64_t* a_rows,
               const uint64_t* a_cols, const void* a_vals, size_t a_nnz, const uint64_t* b_rows, const uint64_t* b_cols,
               const void* b_vals, size_t b_nnz, const uint64_t* c_rows, const uint64_t* c_cols, const void* c_vals,
@@ -285,6 +286,29 @@ int emul_r1cs(int field, int mode, size_t num_cons, size_t num_vars, size_t num_
   std::memcpy(val.data(), csr.val.data(), csr.val.size());
   CsrView m{csr.row_ptr.data(), csr.col.data(), val.data(), (uint32_t)num_cons, (uint32_t)num_vars, (uint32_t)num_io};
   HostLaunch L;
+  if (mode == 2) {
+    const size_t ncols = num_vars + 1 + num_io;
+    const HostCsc csc = csr_to_csc(csr, ncols);
+    std::vector<fe> cval(csc.val.size() / 32 + 1), eq(num_cons), coef(3), eq3(3 * num_cons);
+    std::memcpy(cval.data(), csc.val.data(), csc.val.size());
+    std::memcpy(eq.data(), W1, num_cons * 32);
+    std::memcpy(coef.data(), u1, 96);
+    std::vector<uint32_t> heavy(csc.heavy);
+    heavy.push_back(0);
+    CscView v{csc.col_ptr.data(), csc.srow.data(), cval.data(), heavy.data(), HostCsc::HEAVY};
+    fe* o = (fe*)out;
+    const size_t nh = csc.heavy.size();
+    if (field == 0) {
+      L.run(3 * num_cons, ScaleRowsFn<Fp>{eq.data(), coef.data(), (uint32_t)num_cons, eq3.data()});
+      L.run(ncols, BindRowsFn<Fp>{v, eq3.data(), o});
+      L.run(nh * 32, BindHeavyFn<Fp>{v, eq3.data(), o});
+    } else {
+      L.run(3 * num_cons, ScaleRowsFn<Fq>{eq.data(), coef.data(), (uint32_t)num_cons, eq3.data()});
+      L.run(ncols, BindRowsFn<Fq>{v, eq3.data(), o});
+      L.run(nh * 32, BindHeavyFn<Fq>{v, eq3.data(), o});
+    }
+    return (int)nh;   // number of heavy columns (the test wants the warp path exercised)
+  }
   std::vector<fe> w1(num_vars + 1), w2(num_vars + 1), ux1(1 + num_io), ux2(1 + num_io);
   std::memcpy(w1.data(), W1, num_vars * 32);
   std::memcpy(ux1.data(), u1, 32);

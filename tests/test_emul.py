@@ -274,3 +274,27 @@ def test_msm_affine_rounds(emul, table):
         assert _msm(emul, 0, table, 8, 16, 4, 3, pts[:1], [0]) == bytes(96)
     finally:
         emul.emul_set_affine(0, 0)
+
+
+@pytest.mark.parametrize("fid", [O.FIELD_FQ, O.FIELD_FP])
+def test_r1cs_bind_rows(emul, fid):
+    """ScaleRowsFn + BindRowsFn + BindHeavyFn (the inner sum-check's table) on the CPU against the oracle; t = 80 gives
+    the constant column more than 64 entries, i.e. the heavy-column kernel runs."""
+    vdf = O.MinRootVDF(fid)
+    m = vdf.m
+    rng = O.XorShiftRng()
+    shape, W, X, _ = O.make_step_instance(fid, 80, O.State(3, 4, 80), aug_cons=25)
+    coo = O.shape_to_coo_bytes(shape)
+    keep = [aligned(x) for trip in coo for x in trip[:3]]
+    args = []
+    for k, trip in enumerate(coo):
+        args += [ptr(keep[3 * k]), ptr(keep[3 * k + 1]), ptr(keep[3 * k + 2]), SZ(trip[3])]
+    eq = rand_scalars(rng, m, shape.num_cons)
+    r_abc = rand_scalars(rng, m, 3)
+    eqb, rb = aligned(O.fes_to_bytes(eq, m)), aligned(O.fes_to_bytes(r_abc, m))
+    dummy = aligned(bytes(32 * max(1, shape.num_io)))
+    out = np.zeros((shape.num_vars + 1 + shape.num_io) * 32, np.uint8)
+    heavy = emul.emul_r1cs(fid, 2, SZ(shape.num_cons), SZ(shape.num_vars), SZ(shape.num_io), *args,
+                           ptr(eqb), ptr(rb), ptr(dummy), ptr(eqb), ptr(dummy), ptr(out))
+    assert heavy >= 1
+    assert O.fes_from_bytes(out.tobytes(), m) == shape.bind_rows(eq, r_abc)
