@@ -536,7 +536,55 @@ def sumcheck_measurements(lib, _lib, torch, ell=24):
                "note": "vdfgpu_points_lincomb, host points in and out (9.4 MB up, 4.7 MB down), two 255-bit scalars per output"}
     except Exception as e:
         ipa = {"error": repr(e)}
-    return {"ell": ell, "entries": n, "rounds_called_back": len(calls) // (reps + 2), "ipa_generator_fold": ipa,
+    rounds_cb = len(calls) // (reps + 2)
+    # the same phases at the size of the largest Nova circuit (t = 16384: 59k constraints -> 2^16-entry outer tables,
+    # 75k columns -> 2^17-entry inner tables): launch-bound there; tables are random (the time depends on sizes only),
+    # the transposed product runs on the real step shape
+    nova = {}
+    try:
+        from vdf_b200 import encoding as E, nova as N, synthetic as S
+        cons, nvars, io, A, Bm, C, W, X = S.step_instance(E.FQ, 16384, 9800, seed=42)
+        gs = N.R1CSShape(E.FQ, cons, nvars, io, A, Bm, C)
+        ncols = nvars + 1 + io
+        ex, ey = max(1, (cons - 1).bit_length()), max(1, (ncols - 1).bit_length())
+        eqr, r3 = rand_fe_dev(torch, cons), rand_fe_dev(torch, 3)
+        scratch = torch.zeros((3 * cons, 4), dtype=torch.int64, device="cuda")
+        Mt = torch.zeros((1 << ey, 4), dtype=torch.int64, device="cuda")
+        t_br = cuda_timed(torch, lambda: _lib.check(lib.vdfgpu_r1cs_bind_rows_dev(gs._h, eqr.data_ptr(), r3.data_ptr(), scratch.data_ptr(), Mt.data_ptr())))
+
+        def wall(fn_, reps_=3):
+            best = None
+            for _ in range(reps_):
+                torch.cuda.synchronize()
+                t0_ = time.perf_counter()
+                fn_()
+                d_ = time.perf_counter() - t0_
+                best = d_ if best is None or d_ < best else best
+            return best
+
+        def outer():
+            tb = [rand_fe_dev(torch, 1 << ex) for _ in range(4)]
+            torch.cuda.synchronize()
+            t0_ = time.perf_counter()
+            _lib.check(lib.vdfgpu_sumcheck_cubic_dev(1, *[t.data_ptr() for t in tb], ex, ctypes.cast(fn, ctypes.c_void_p), None, final))
+            return time.perf_counter() - t0_
+
+        def inner():
+            tb = [rand_fe_dev(torch, 1 << ey) for _ in range(2)]
+            torch.cuda.synchronize()
+            t0_ = time.perf_counter()
+            _lib.check(lib.vdfgpu_sumcheck_quad_dev(1, tb[0].data_ptr(), tb[1].data_ptr(), ey, ctypes.cast(fn, ctypes.c_void_p), None, final))
+            return time.perf_counter() - t0_
+
+        t_out = min(outer() for _ in range(4))
+        t_in = min(inner() for _ in range(4))
+        nova = {"t": 16384, "cons": cons, "cols": ncols, "outer_cubic_ms": t_out * 1e3, "outer_rounds": ex,
+                "bind_rows_ms": t_br * 1e3, "inner_quad_ms": t_in * 1e3, "inner_rounds": ey,
+                "note": "wall clock incl. one 96-byte read-back + trivial host callback per round; bind_rows by CUDA events"}
+        gs.close()
+    except Exception as e:
+        nova = {"error": repr(e)}
+    return {"ell": ell, "entries": n, "rounds_called_back": rounds_cb, "ipa_generator_fold": ipa, "nova_size": nova,
             "cubic": {"ms": dt * 1e3, "algorithmic_bytes": alg, "achieved_gbs": alg / dt / 1e9, "frac_of_hbm": alg / dt / 1e9 / peak,
                       "field_mul_per_s": 10 * n / dt},
             "quad": {"ms": dq * 1e3, "algorithmic_bytes": algq, "achieved_gbs": algq / dq / 1e9, "frac_of_hbm": algq / dq / 1e9 / peak},
