@@ -24,11 +24,19 @@ static void eq_evals_enqueue(CudaLaunch& L, const fe* r_dev, size_t ell, fe* out
   L.free(lo);
 }
 
-struct ScScratch {   // per-call device scratch of the round loop
+struct ScScratch {   // per-call device scratch of the round loop (stream-ordered pool allocations)
   fe* partial = nullptr;   // [grid][3]
   fe* evals = nullptr;     // [4]
-  fe* r = nullptr;
 };
+
+// Pinned landing zone of the per-round read-backs, one per calling thread: at Nova sizes a round is two small kernels,
+// so what a round costs is the round trip to the caller's transcript -- a pageable 96-byte copy is staged by the driver
+// (about 10 us), a pinned one is a plain DMA.
+static fe* pinned_evals() {
+  static thread_local fe* p = nullptr;
+  if (!p) VDF_CUDA_CHECK(cudaHostAlloc((void**)&p, 8 * sizeof(fe), cudaHostAllocDefault));
+  return p;
+}
 
 template <class F>
 static void cubic_round_enqueue(cudaStream_t st, const PolySet& P, size_t half, const ScScratch& s) {
@@ -67,9 +75,8 @@ static int sumcheck_run(int field, PolySet P, int n_polys, size_t ell, vdfgpu_ro
   ScScratch s;
   int rc = guarded([&] {
     require_ready();
-    VDF_CUDA_CHECK(cudaMalloc((void**)&s.partial, (size_t)148 * 8 * 3 * sizeof(fe)));
-    VDF_CUDA_CHECK(cudaMalloc((void**)&s.evals, 4 * sizeof(fe)));
-    VDF_CUDA_CHECK(cudaMalloc((void**)&s.r, sizeof(fe)));
+    VDF_CUDA_CHECK(cudaMallocAsync((void**)&s.partial, (size_t)148 * 8 * 3 * sizeof(fe), cur_stream()));
+    VDF_CUDA_CHECK(cudaMallocAsync((void**)&s.evals, 4 * sizeof(fe), cur_stream()));
   });
   size_t len = (size_t)1 << ell;
   for (size_t round = 0; rc == VDFGPU_OK && round < ell; round++) {
@@ -85,8 +92,10 @@ static int sumcheck_run(int field, PolySet P, int n_polys, size_t ell, vdfgpu_ro
         if (field == VDFGPU_FP) quad_round_enqueue<Fp>(st, P, half, s);
         else quad_round_enqueue<Fq>(st, P, half, s);
       }
-      d2h(evals, s.evals, n_evals * sizeof(fe), st);   // pageable destination: complete on return
+      fe* pin = pinned_evals();
+      VDF_CUDA_CHECK(cudaMemcpyAsync(pin, s.evals, n_evals * sizeof(fe), cudaMemcpyDeviceToHost, st));
       VDF_CUDA_CHECK(cudaStreamSynchronize(st));
+      for (int k = 0; k < n_evals; k++) evals[k] = pin[k];
     });
     if (rc != VDFGPU_OK) break;
     if (fn(user, round, evals, (size_t)n_evals, &r) != 0) {   // the caller's transcript: outside the lock
@@ -97,10 +106,9 @@ static int sumcheck_run(int field, PolySet P, int n_polys, size_t ell, vdfgpu_ro
     rc = guarded([&] {
       require_ready();
       cudaStream_t st = cur_stream();
-      h2d(s.r, &r, sizeof(fe), st);
       CudaLaunch L(st);
-      if (field == VDFGPU_FP) L.run<256>((size_t)n_polys * half, BindTopFn<Fp>{P, half, s.r});
-      else L.run<256>((size_t)n_polys * half, BindTopFn<Fq>{P, half, s.r});
+      if (field == VDFGPU_FP) L.run<256>((size_t)n_polys * half, BindTopValFn<Fp>{P, half, r});
+      else L.run<256>((size_t)n_polys * half, BindTopValFn<Fq>{P, half, r});
       ctx().launches += L.launches;
     });
     len = half;
@@ -109,14 +117,17 @@ static int sumcheck_run(int field, PolySet P, int n_polys, size_t ell, vdfgpu_ro
     rc = guarded([&] {
       require_ready();
       cudaStream_t st = cur_stream();
-      for (int q = 0; q < n_polys; q++) d2h((uint8_t*)final_host + 32 * q, P.p[q], sizeof(fe), st);
+      fe* pin = pinned_evals();
+      for (int q = 0; q < n_polys; q++)
+        VDF_CUDA_CHECK(cudaMemcpyAsync(pin + q, P.p[q], sizeof(fe), cudaMemcpyDeviceToHost, st));
       VDF_CUDA_CHECK(cudaStreamSynchronize(st));
+      std::memcpy(final_host, pin, 32 * (size_t)n_polys);
     });
   std::string keep = rc == VDFGPU_OK ? std::string() : std::string(vdfgpu_last_error());
   guarded([&] {
     if (ctx().ready) {
-      cudaStreamSynchronize(cur_stream());
-      cudaFree(s.partial); cudaFree(s.evals); cudaFree(s.r);
+      if (s.partial) cudaFreeAsync(s.partial, cur_stream());
+      if (s.evals) cudaFreeAsync(s.evals, cur_stream());
     }
   });
   if (rc != VDFGPU_OK) set_error(keep);

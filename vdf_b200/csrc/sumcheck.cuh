@@ -141,6 +141,20 @@ struct BindTopFn {
   }
 };
 
+// BindTopFn with the challenge as a kernel argument: the round loop has it on the host, one upload fewer per round
+template <class F>
+struct BindTopValFn {
+  PolySet polys;
+  size_t half;
+  fe r;
+  VDF_HD void operator()(size_t idx) const {
+    const size_t q = idx / half, i = idx - q * half;
+    fe* P = polys.p[q];
+    const fe lo = fe_load(P + i), hi = fe_load(P + half + i);
+    fe_store(P + i, F::add(lo, F::mul(r, F::sub(hi, lo))));
+  }
+};
+
 #if defined(__CUDACC__)
 // ---- reductions ------------------------------------------------------------------------------------------
 template <class F>
