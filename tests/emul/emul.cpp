@@ -301,11 +301,11 @@ int emul_r1cs(int field, int mode, size_t num_cons, size_t num_vars, size_t num_
     if (field == 0) {
       L.run(3 * num_cons, ScaleRowsFn<Fp>{eq.data(), coef.data(), (uint32_t)num_cons, eq3.data()});
       L.run(ncols, BindRowsFn<Fp>{v, eq3.data(), o});
-      L.run(nh * 32, BindHeavyFn<Fp>{v, eq3.data(), o});
+      L.run(nh * BindHeavyFn<Fp>::THREADS, BindHeavyFn<Fp>{v, eq3.data(), o});
     } else {
       L.run(3 * num_cons, ScaleRowsFn<Fq>{eq.data(), coef.data(), (uint32_t)num_cons, eq3.data()});
       L.run(ncols, BindRowsFn<Fq>{v, eq3.data(), o});
-      L.run(nh * 32, BindHeavyFn<Fq>{v, eq3.data(), o});
+      L.run(nh * BindHeavyFn<Fq>::THREADS, BindHeavyFn<Fq>{v, eq3.data(), o});
     }
     return (int)nh;   // number of heavy columns (the test wants the warp path exercised)
   }

@@ -271,11 +271,11 @@ static void launch_bind_rows(CudaLaunch& L, const vdfgpu_r1cs* s, const fe* eq, 
   if (s->field == VDFGPU_FP) {
     L.run<128>(3 * (size_t)s->cons, ScaleRowsFn<Fp>{eq, coef, s->cons, eq3});
     L.run<128>(ncols, BindRowsFn<Fp>{v, eq3, out});
-    if (s->n_heavy) L.run<128>((size_t)s->n_heavy * 32, BindHeavyFn<Fp>{v, eq3, out});
+    if (s->n_heavy) L.run<BindHeavyFn<Fp>::THREADS>((size_t)s->n_heavy * BindHeavyFn<Fp>::THREADS, BindHeavyFn<Fp>{v, eq3, out});
   } else {
     L.run<128>(3 * (size_t)s->cons, ScaleRowsFn<Fq>{eq, coef, s->cons, eq3});
     L.run<128>(ncols, BindRowsFn<Fq>{v, eq3, out});
-    if (s->n_heavy) L.run<128>((size_t)s->n_heavy * 32, BindHeavyFn<Fq>{v, eq3, out});
+    if (s->n_heavy) L.run<BindHeavyFn<Fq>::THREADS>((size_t)s->n_heavy * BindHeavyFn<Fq>::THREADS, BindHeavyFn<Fq>{v, eq3, out});
   }
 }
 

@@ -120,8 +120,8 @@ struct CrossTermFn {
 // compute_eval_table_sparse combined with the three challenges [R], reached from CompressedSNARK::prove
 // (src/nova/proof.rs:363).  The scaled row table eq3[mat * cons + x] = r_mat * eq(x) first, then one THREAD per column
 // over the column view (40 bytes per entry read in order + one gathered table element); the few heavy columns (the
-// constant column of the step circuit holds one entry per round) are left to one WARP each: lanes stride over the
-// entries, a shuffle tree adds the lanes.
+// constant column of the step circuit holds one entry per round, with a full-size coefficient) are left to one BLOCK
+// each: threads stride over the entries, shuffle trees and shared memory add them up.
 struct CscView {
   const uint32_t* col_ptr;  // [ncols + 1]
   const uint32_t* srow;     // stacked row = mat * cons + row
@@ -159,18 +159,22 @@ struct BindRowsFn {   // index = column
 };
 
 template <class F>
-struct BindHeavyFn {   // index = (position in the heavy list) * 32 + lane; launched with whole warps
+struct BindHeavyFn {   // index = (position in the heavy list) * THREADS + thread; launched with whole blocks of THREADS
+  static constexpr uint32_t THREADS = 512;
   CscView m;
   const fe* eq3;
   fe* out;
   VDF_HD void operator()(size_t idx) const {
-    const uint32_t col = m.heavy[idx >> 5];
+    const uint32_t col = m.heavy[idx / THREADS];
     const uint32_t lo = m.col_ptr[col], hi = m.col_ptr[col + 1];
     const fe one = F::one(), minus_one = F::neg(F::one());
     fe acc = F::zero();
 #if defined(__CUDA_ARCH__)
-    const unsigned lane = (unsigned)idx & 31u;
-    for (uint32_t k = lo + lane; k < hi; k += 32)
+    // the constant column of a t-round step circuit has ~3t entries with full-size coefficients: one multiplication
+    // each, spread over the block; shuffle tree per warp, then the warp totals through shared memory
+    __shared__ fe warp_tot[THREADS / 32];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    for (uint32_t k = lo + tid; k < hi; k += THREADS)
       acc = mul_acc<F>(acc, fe_load(m.val + k), fe_load_gather(eq3 + m.srow[k]), one, minus_one);
 #pragma unroll 1
     for (int d = 16; d >= 1; d >>= 1) {
@@ -179,9 +183,21 @@ struct BindHeavyFn {   // index = (position in the heavy list) * 32 + lane; laun
       for (int q = 0; q < 8; q++) o.v[q] = __shfl_down_sync(0xffffffffu, acc.v[q], d);
       acc = F::add(acc, o);
     }
-    if (lane == 0) fe_store(out + col, acc);
+    if (lane == 0) warp_tot[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+      acc = lane < THREADS / 32 ? warp_tot[lane] : F::zero();
+#pragma unroll 1
+      for (int d = 8; d >= 1; d >>= 1) {
+        fe o;
+#pragma unroll
+        for (int q = 0; q < 8; q++) o.v[q] = __shfl_down_sync(0xffffffffu, acc.v[q], d);
+        acc = F::add(acc, o);
+      }
+      if (lane == 0) fe_store(out + col, acc);
+    }
 #else
-    if (idx & 31) return;
+    if (idx % THREADS) return;
     for (uint32_t k = lo; k < hi; k++) acc = mul_acc<F>(acc, fe_load(m.val + k), fe_load(eq3 + m.srow[k]), one, minus_one);
     fe_store(out + col, acc);
 #endif
