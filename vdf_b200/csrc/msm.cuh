@@ -1175,12 +1175,13 @@ void msm_accumulate(L& L_, const MsmPlan& p, const affine_t* pts, const ScalarSe
   // additions, and the owner pass is serial in the number of pieces of the heaviest bucket): G = 8, run
   // the levels down to 256 records.
   if (p.rec_warp) {
+    const bool long_runs = n_rec > 2 * (size_t)NBK;
+#ifdef VDF_NO_QUAD
+    // (the lane-per-addition levels of round 2's second pass, kept for A/B builds)
     // one warp per 32 records (RecWarpLevelFn): 16x fewer records per level with a chain of 5 additions; down to 64
     // records so that the serial owner pass stays short even when one bucket owns every remaining piece
     // The warp level spends 5 lane-additions per record where the serial one spends 1: with many records in long
     // runs (several pieces per bucket) the first levels are throughput-bound, so they stay serial (G = 8).
-    const bool long_runs = n_rec > 2 * (size_t)NBK;
-#ifdef VDF_NO_QUAD
     while (n_rec > 64) {
       const bool serial = long_runs && n_rec > 65536;
       const size_t per = serial ? 8 : 32;
